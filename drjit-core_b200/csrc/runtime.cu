@@ -1,0 +1,395 @@
+// runtime.cu -- minimal runtime around the primitive kernels: device / stream
+// bookkeeping, error reporting, allocation, copies and typed fills.
+//
+// Replaces, for this path only: jitc_cuda_init (src/cuda_core.cpp:266-539, no
+// blob decompression / lazy PTX JIT any more -- the sm_100a SASS is linked into
+// this library), jitc_malloc's rounding contract (src/malloc.cpp:113-124),
+// CUDAThreadState::memset_async / memcpy(_async) (src/cuda_ts.cpp:129-183,
+// :977-990) and the fill_64 kernel (resources/misc.cuh:28-32).
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace b200 {
+
+static thread_local std::string tls_error;
+
+struct DeviceState {
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+};
+
+static std::mutex g_lock;
+static bool g_initialised = false;
+static std::vector<DeviceState> g_devices;
+static std::atomic<uint64_t> g_launches{ 0 };
+// pointer -> kind (0 device, 1 pinned host) for b200_free
+static std::unordered_map<void *, int> g_allocs;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list args;
+    va_start(args, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, args);
+    va_end(args);
+    tls_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t err, const char *what) {
+    if (err == cudaSuccess)
+        return B200_OK;
+    return fail(B200_ERR_CUDA, "CUDA error %d (%s) in %s", (int) err,
+                cudaGetErrorString(err), what);
+}
+
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+const char *type_name(int vt) {
+    // src/var.cpp type_name table
+    static const char *names[16] = { "void", "bool", "?", "int8", "uint8", "int16",
+        "uint16", "int32", "uint32", "int64", "uint64", "pointer", "?", "float16",
+        "float32", "float64" };
+    return (vt >= 0 && vt < 16) ? names[vt] : "?";
+}
+
+const char *op_name(int op) {
+    static const char *names[7] = { "none", "add", "mul", "min", "max", "and", "or" };
+    return (op >= 0 && op < 7) ? names[op] : "?";
+}
+
+// The CUDA runtime's current device of the calling thread is the single source
+// of truth (b200_set_device == cudaSetDevice + lazy per-device setup), so the
+// library follows whatever device the host program -- e.g. torch -- selected.
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return dev;
+}
+
+int ensure_init() {
+    if (g_initialised)
+        return B200_OK;
+    return b200_init();
+}
+
+static int prepare_device(int dev) {
+    DeviceState &d = g_devices[dev];
+    if (d.stream)
+        return B200_OK;
+    std::lock_guard<std::mutex> guard(g_lock);
+    if (d.stream)
+        return B200_OK;
+    if (d.cc_major < 10)
+        return fail(B200_ERR_CUDA,
+                    "b200: device %d has compute capability %d.%d; the kernels in "
+                    "this library are built for sm_100a only",
+                    dev, d.cc_major, d.cc_minor);
+    B200_CUDA_CHECK(cudaSetDevice(dev));
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    // keep freed temporaries cached in the pool (jitc_malloc caches as well)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    return B200_OK;
+}
+
+cudaStream_t resolve_stream(void *stream) {
+    if (stream)
+        return (cudaStream_t) stream;
+    int dev = current_device();
+    if (dev >= 0 && dev < (int) g_devices.size() && prepare_device(dev) == B200_OK)
+        return g_devices[dev].stream;
+    return nullptr;
+}
+
+int sm_count() {
+    int dev = current_device();
+    if (dev >= 0 && dev < (int) g_devices.size())
+        return g_devices[dev].sm_count;
+    return 148;
+}
+
+void *temp_alloc(size_t bytes, cudaStream_t stream) {
+    void *ptr = nullptr;
+    if (bytes == 0)
+        bytes = 16;
+    if (cudaMallocAsync(&ptr, bytes, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return ptr;
+}
+
+void temp_free(void *ptr, cudaStream_t stream) {
+    if (ptr)
+        cudaFreeAsync(ptr, stream);
+}
+
+// Typed fill: 'count' elements of 2 / 4 / 8 bytes.  16-byte stores in the body,
+// element stores for the unaligned head and the tail.
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(T *ptr, uint64_t count, T value) {
+    constexpr uint32_t N = 16 / sizeof(T);
+    uint64_t head = ((16 - ((uintptr_t) ptr & 15)) & 15) / sizeof(T);
+    if (head > count)
+        head = count;
+    uint64_t nvec = (count - head) / N;
+    uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x,
+             stride = (uint64_t) gridDim.x * blockDim.x;
+    Vec16<T> v;
+    #pragma unroll
+    for (uint32_t i = 0; i < N; ++i)
+        v.elem[i] = value;
+    uint4 *body = (uint4 *) (ptr + head);
+    for (uint64_t i = tid; i < nvec; i += stride)
+        st_stream(body + i, v.raw);
+    uint64_t tail_start = head + nvec * N;
+    for (uint64_t i = tid; i < head; i += stride)
+        ptr[i] = value;
+    for (uint64_t i = tail_start + tid; i < count; i += stride)
+        ptr[i] = value;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_init(void) {
+    std::lock_guard<std::mutex> guard(g_lock);
+    if (g_initialised)
+        return B200_OK;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(B200_ERR_CUDA,
+                    "b200_init(): no CUDA device available (%s); this library has "
+                    "no CPU fallback",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    g_devices.resize(count);
+    for (int i = 0; i < count; ++i) {
+        cudaDeviceProp prop;
+        B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, i));
+        g_devices[i].sm_count = prop.multiProcessorCount;
+        g_devices[i].cc_major = prop.major;
+        g_devices[i].cc_minor = prop.minor;
+        // Streams / pools are created lazily per device on first selection so
+        // that a rank of a multi-process job only ever touches its own GPU.
+    }
+    cudaSetDevice(prev);
+    g_initialised = true;
+    return B200_OK;
+}
+
+
+int b200_shutdown(void) {
+    std::lock_guard<std::mutex> guard(g_lock);
+    if (!g_initialised)
+        return B200_OK;
+    for (size_t i = 0; i < g_devices.size(); ++i) {
+        if (g_devices[i].stream) {
+            cudaSetDevice((int) i);
+            cudaStreamSynchronize(g_devices[i].stream);
+            cudaStreamDestroy(g_devices[i].stream);
+            g_devices[i].stream = nullptr;
+        }
+    }
+    g_devices.clear();
+    g_initialised = false;
+    return B200_OK;
+}
+
+const char *b200_last_error(void) { return tls_error.c_str(); }
+
+int b200_device_count(void) {
+    if (ensure_init())
+        return 0;
+    return (int) g_devices.size();
+}
+
+int b200_set_device(int device) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    if (device < 0 || device >= (int) g_devices.size())
+        return fail(B200_ERR_INVALID, "b200_set_device(%d): must be in the range 0..%d!",
+                    device, (int) g_devices.size() - 1);
+    B200_CUDA_CHECK(cudaSetDevice(device));
+    return prepare_device(device);
+}
+
+int b200_device(void) {
+    if (ensure_init())
+        return -1;
+    return current_device();
+}
+
+void *b200_stream(void) {
+    if (ensure_init())
+        return nullptr;
+    int dev = current_device();
+    if (prepare_device(dev))
+        return nullptr;
+    return (void *) g_devices[dev].stream;
+}
+
+int b200_sm_count(void) {
+    if (ensure_init())
+        return 0;
+    return sm_count();
+}
+
+int b200_sync(void *stream) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    cudaStream_t s = stream ? (cudaStream_t) stream : (cudaStream_t) b200_stream();
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+    return B200_OK;
+}
+
+void *b200_malloc(size_t size, int kind) {
+    if (ensure_init() || size == 0)
+        return nullptr;
+    // src/malloc.cpp:113-124: round up to 64 bytes, then to a power of two
+    size = (size + 63) / 64 * 64;
+    size_t rounded = 64;
+    while (rounded < size)
+        rounded <<= 1;
+    void *ptr = nullptr;
+    cudaError_t err = kind == 1 ? cudaMallocHost(&ptr, rounded) : cudaMalloc(&ptr, rounded);
+    if (err != cudaSuccess) {
+        cuda_fail(err, kind == 1 ? "cudaMallocHost" : "cudaMalloc");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> guard(g_lock);
+    g_allocs[ptr] = kind;
+    return ptr;
+}
+
+int b200_free(void *ptr) {
+    if (!ptr)
+        return B200_OK;
+    int kind = -1;
+    {
+        std::lock_guard<std::mutex> guard(g_lock);
+        auto it = g_allocs.find(ptr);
+        if (it == g_allocs.end())
+            return fail(B200_ERR_INVALID, "b200_free(): unknown address %p!", ptr);
+        kind = it->second;
+        g_allocs.erase(it);
+    }
+    if (kind == 1)
+        B200_CUDA_CHECK(cudaFreeHost(ptr));
+    else
+        B200_CUDA_CHECK(cudaFree(ptr));
+    return B200_OK;
+}
+
+int b200_memcpy(void *dst, const void *src, size_t size) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    // synchronous with respect to the library stream as well (jit_memcpy syncs)
+    cudaStream_t s = (cudaStream_t) b200_stream();
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, size, cudaMemcpyDefault, s));
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+    return B200_OK;
+}
+
+int b200_memcpy_async(void *stream, void *dst, const void *src, size_t size) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    cudaStream_t s = stream ? (cudaStream_t) stream : (cudaStream_t) b200_stream();
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, size, cudaMemcpyDefault, s));
+    return B200_OK;
+}
+
+int b200_memset_async(void *stream, void *ptr, uint64_t size, uint32_t isize,
+                      const void *src) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    if (isize != 1 && isize != 2 && isize != 4 && isize != 8)
+        return fail(B200_ERR_INVALID,
+                    "jit_memset_async(): invalid element size (must be 1, 2, 4, or 8)!");
+    if (size == 0)
+        return B200_OK;
+    cudaStream_t s = stream ? (cudaStream_t) stream : (cudaStream_t) b200_stream();
+
+    // Patterns whose bytes are all equal collapse to a byte memset
+    // (src/cuda_ts.cpp:143-148 does this for zero only)
+    const uint8_t *b = (const uint8_t *) src;
+    bool uniform = true;
+    for (uint32_t i = 1; i < isize; ++i)
+        uniform &= b[i] == b[0];
+    if (uniform) {
+        B200_CUDA_CHECK(cudaMemsetAsync(ptr, b[0], size * isize, s));
+        return B200_OK;
+    }
+
+    if (((uintptr_t) ptr) % isize != 0)
+        return fail(B200_ERR_INVALID, "jit_memset_async(): misaligned address %p!", ptr);
+
+    uint64_t vecs = size * isize / 16 + 1;
+    uint32_t blocks = (uint32_t) std::min<uint64_t>(ceil_div(vecs, 256), (uint64_t) sm_count() * 8);
+    switch (isize) {
+        case 2: { uint16_t v; memcpy(&v, src, 2); fill_kernel<uint16_t><<<blocks, 256, 0, s>>>((uint16_t *) ptr, size, v); break; }
+        case 4: { uint32_t v; memcpy(&v, src, 4); fill_kernel<uint32_t><<<blocks, 256, 0, s>>>((uint32_t *) ptr, size, v); break; }
+        case 8: { uint64_t v; memcpy(&v, src, 8); fill_kernel<uint64_t><<<blocks, 256, 0, s>>>((uint64_t *) ptr, size, v); break; }
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+uint64_t b200_reduce_identity(int vt, int op) {
+    // src/var.cpp:140-166 and :2642-2652
+    static const uint64_t all_ones[16] = {
+        0, 1, 0, 0xff, 0xff, 0xffff, 0xffff, 0xffffffffu, 0xffffffffu,
+        ~0ull, ~0ull, ~0ull, 0, 0xffff, 0xffffffffu, ~0ull };
+    static const uint64_t one[16] = {
+        0, 1, 0, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0x3c00, 0x3f800000,
+        0x3ff0000000000000ull };
+    static const uint64_t tmin[16] = {
+        0, 0, 0, 0x80, 0, 0x8000, 0, 0x80000000u, 0, 0x8000000000000000ull, 0, 0,
+        0, 0xfc00, 0xff800000u, 0xfff0000000000000ull };
+    static const uint64_t tmax[16] = {
+        0, 1, 0, 0x7f, 0xff, 0x7fff, 0xffff, 0x7fffffff, 0xffffffffu,
+        0x7fffffffffffffffull, ~0ull, ~0ull, 0, 0x7c00, 0x7f800000,
+        0x7ff0000000000000ull };
+    if (vt < 0 || vt >= 16)
+        return 0;
+    switch (op) {
+        case B200_OP_OR:
+        case B200_OP_ADD: return 0;
+        case B200_OP_AND: return all_ones[vt];
+        case B200_OP_MUL: return one[vt];
+        case B200_OP_MIN: return tmax[vt];
+        case B200_OP_MAX: return tmin[vt];
+        default: return 0;
+    }
+}
+
+uint64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+} // extern "C"

@@ -1,0 +1,296 @@
+// scatter.cu -- atomic scatter-reduce: target[index[i]] op= value[i].
+//
+// Stand-alone form of what the reference splices into its JIT-generated fused
+// kernels as PTX text: jitc_cuda_render_scatter_reduce
+// (src/cuda_scatter.cpp:246-354), the warp pre-reduction
+// jitc_cuda_render_warp_reduce (:125-244), float min/max emulation through
+// signed/unsigned integer atomics (:74-106) and the f16x2 packing trick for
+// half precision (:283-339).
+//
+// Modes (jit.h:1017-1066):
+//   Direct       one red.global per element;
+//   Local        lanes that hit the same address are found with match.any and
+//                merged by a rank-halving tree; the lowest lane issues the
+//                single atomic (Auto resolves to this, as in the reference's
+//                default flag set);
+//   NoConflicts  plain load / op / store.
+#include "common.cuh"
+
+namespace b200 {
+
+static constexpr int SCATTER_THREADS = 256;
+
+// ---- atomic primitives (result unused -> RED instructions) ------------------
+
+template <typename T, int Op> struct Atomic;
+
+#define B200_ATOMIC_INT(T, CT)                                                                  \
+    template <> struct Atomic<T, B200_OP_ADD> { static B200_DEVICE void apply(T *p, T v) { atomicAdd((CT *) p, (CT) v); } }; \
+    template <> struct Atomic<T, B200_OP_MIN> { static B200_DEVICE void apply(T *p, T v) { atomicMin(p, v); } }; \
+    template <> struct Atomic<T, B200_OP_MAX> { static B200_DEVICE void apply(T *p, T v) { atomicMax(p, v); } }; \
+    template <> struct Atomic<T, B200_OP_AND> { static B200_DEVICE void apply(T *p, T v) { atomicAnd((CT *) p, (CT) v); } }; \
+    template <> struct Atomic<T, B200_OP_OR>  { static B200_DEVICE void apply(T *p, T v) { atomicOr((CT *) p, (CT) v); } };
+
+B200_ATOMIC_INT(uint32_t, unsigned int)
+B200_ATOMIC_INT(int32_t, unsigned int)
+B200_ATOMIC_INT(unsigned long long, unsigned long long)
+B200_ATOMIC_INT(long long, unsigned long long)
+
+template <> struct Atomic<float, B200_OP_ADD> { static B200_DEVICE void apply(float *p, float v) { atomicAdd(p, v); } };
+template <> struct Atomic<double, B200_OP_ADD> { static B200_DEVICE void apply(double *p, double v) { atomicAdd(p, v); } };
+
+// Float min/max: IEEE bit patterns order like signed integers when the sign
+// bit is clear and like unsigned integers in reverse when it is set.
+template <> struct Atomic<float, B200_OP_MIN> {
+    static B200_DEVICE void apply(float *p, float v) {
+        int bits = __float_as_int(v);
+        if (bits >= 0) atomicMin((int *) p, bits);
+        else atomicMax((unsigned int *) p, (unsigned int) bits);
+    }
+};
+template <> struct Atomic<float, B200_OP_MAX> {
+    static B200_DEVICE void apply(float *p, float v) {
+        int bits = __float_as_int(v);
+        if (bits >= 0) atomicMax((int *) p, bits);
+        else atomicMin((unsigned int *) p, (unsigned int) bits);
+    }
+};
+template <> struct Atomic<double, B200_OP_MIN> {
+    static B200_DEVICE void apply(double *p, double v) {
+        long long bits = __double_as_longlong(v);
+        if (bits >= 0) atomicMin((long long *) p, bits);
+        else atomicMax((unsigned long long *) p, (unsigned long long) bits);
+    }
+};
+template <> struct Atomic<double, B200_OP_MAX> {
+    static B200_DEVICE void apply(double *p, double v) {
+        long long bits = __double_as_longlong(v);
+        if (bits >= 0) atomicMax((long long *) p, bits);
+        else atomicMin((unsigned long long *) p, (unsigned long long) bits);
+    }
+};
+
+// Half precision: there is no scalar f16 atomic; operate on the enclosing
+// aligned f16x2 word with the identity in the other half.
+template <int Op> B200_DEVICE void atomic_f16x2(__half *p, __half v, unsigned short identity) {
+    uintptr_t addr = (uintptr_t) p;
+    bool upper = (addr & 2) != 0;
+    unsigned short vb = __half_as_ushort(v);
+    unsigned short lo = upper ? identity : vb, hi = upper ? vb : identity;
+    void *word = (void *) (addr & ~(uintptr_t) 2);
+    if constexpr (Op == B200_OP_ADD) {
+        uint32_t packed = ((uint32_t) hi << 16) | lo;
+        asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(word), "r"(packed) : "memory");
+    } else if constexpr (Op == B200_OP_MIN) {
+        // sm_90+ vector form (the reference emits the same, cuda_scatter.cpp:307-332)
+        asm volatile("red.global.v2.f16.min.noftz [%0], {%1, %2};" :: "l"(word), "h"(lo), "h"(hi) : "memory");
+    } else {
+        asm volatile("red.global.v2.f16.max.noftz [%0], {%1, %2};" :: "l"(word), "h"(lo), "h"(hi) : "memory");
+    }
+}
+template <> struct Atomic<__half, B200_OP_ADD> { static B200_DEVICE void apply(__half *p, __half v) { atomic_f16x2<B200_OP_ADD>(p, v, 0x0000); } };
+template <> struct Atomic<__half, B200_OP_MIN> { static B200_DEVICE void apply(__half *p, __half v) { atomic_f16x2<B200_OP_MIN>(p, v, 0x7c00); } };
+template <> struct Atomic<__half, B200_OP_MAX> { static B200_DEVICE void apply(__half *p, __half v) { atomic_f16x2<B200_OP_MAX>(p, v, 0xfc00); } };
+
+// Operator in the element type itself (the pre-reduction of the reference runs
+// in the element type as well, half included: src/cuda_scatter.cpp:133-135)
+template <typename T, int Op> struct ElemOp {
+    static B200_DEVICE T apply(T a, T b) { return Red<T, Op>::apply(a, b); }
+};
+template <int Op> struct ElemOp<__half, Op> {
+    static B200_DEVICE __half apply(__half a, __half b) {
+        if constexpr (Op == B200_OP_ADD) return __hadd(a, b);
+        else if constexpr (Op == B200_OP_MIN) return __hmin(a, b);
+        else return __hmax(a, b);
+    }
+};
+
+template <typename T> B200_DEVICE T shfl_elem(uint32_t mask, T v, int src) {
+    if constexpr (sizeof(T) == 8) {
+        uint64_t u; memcpy(&u, &v, 8);
+        uint32_t lo = __shfl_sync(mask, (uint32_t) u, src), hi = __shfl_sync(mask, (uint32_t) (u >> 32), src);
+        u = ((uint64_t) hi << 32) | lo;
+        T r; memcpy(&r, &u, 8); return r;
+    } else if constexpr (sizeof(T) == 4) {
+        uint32_t u; memcpy(&u, &v, 4);
+        u = __shfl_sync(mask, u, src);
+        T r; memcpy(&r, &u, 4); return r;
+    } else {
+        unsigned short s; memcpy(&s, &v, 2);
+        uint32_t u = __shfl_sync(mask, (uint32_t) s, src);
+        s = (unsigned short) u;
+        T r; memcpy(&r, &s, 2); return r;
+    }
+}
+
+template <typename T, int Op, int MODE>
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
+                      const uint32_t *__restrict__ index, const uint8_t *__restrict__ mask,
+                      uint64_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
+    const uint64_t first = (uint64_t) blockIdx.x * SCATTER_THREADS + threadIdx.x;
+    constexpr int U = 4;
+
+    // all lanes of a warp run the same number of iterations (warp collectives)
+    for (uint64_t base = first - lane; base < n; base += stride * U) {
+        T val[U];
+        uint32_t idx[U];
+        bool on[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint64_t i = base + lane + (uint64_t) u * stride;
+            on[u] = i < n;
+            if (on[u]) {
+                idx[u] = __ldcs(index + i);
+                val[u] = __ldcs(value + i);
+                if (mask)
+                    on[u] = __ldcs(mask + i) != 0;
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (base + (uint64_t) u * stride >= n)
+                break; // warp-uniform
+            if constexpr (MODE == B200_MODE_NO_CONFLICTS) {
+                if (on[u]) {
+                    T *p = target + idx[u];
+                    *p = ElemOp<T, Op>::apply(*p, val[u]);
+                }
+            } else if constexpr (MODE == B200_MODE_DIRECT) {
+                if (on[u])
+                    Atomic<T, Op>::apply(target + idx[u], val[u]);
+            } else {
+                uint32_t active = __ballot_sync(FULL_MASK, on[u]);
+                if (on[u]) {
+                    uint32_t peers = __match_any_sync(active, idx[u]);
+                    T v = val[u];
+                    if (__any_sync(active, peers != (1u << lane))) {
+                        // rank-halving tree inside every group of equal addresses:
+                        // each round a lane absorbs the next surviving peer above
+                        // it, then the odd-ranked lanes drop out
+                        uint32_t rank = __popc(peers & ((1u << lane) - 1));
+                        uint32_t above = peers & ~((2u << lane) - 1);
+                        while (__any_sync(active, above != 0)) {
+                            int src = above ? __ffs(above) - 1 : (int) lane;
+                            T other = shfl_elem<T>(active, v, src);
+                            if (above)
+                                v = ElemOp<T, Op>::apply(v, other);
+                            uint32_t even = __ballot_sync(active, (rank & 1) == 0);
+                            above &= even;
+                            rank >>= 1;
+                        }
+                    }
+                    if ((peers & ((1u << lane) - 1)) == 0) // lowest lane of its group
+                        Atomic<T, Op>::apply(target + idx[u], v);
+                }
+            }
+        }
+    }
+}
+
+struct ScatterCall {
+    cudaStream_t stream;
+    void *target;
+    const void *value;
+    const uint32_t *index;
+    const uint8_t *mask;
+    uint64_t n;
+    int mode;
+};
+
+template <typename T, int Op> static int launch_scatter(const ScatterCall &c) {
+    uint32_t grid = (uint32_t) std::max<uint64_t>(
+        1, std::min<uint64_t>(ceil_div(c.n, (uint64_t) SCATTER_THREADS * 4), (uint64_t) sm_count() * 16));
+    T *target = (T *) c.target;
+    const T *value = (const T *) c.value;
+    switch (c.mode) {
+        case B200_MODE_DIRECT:
+            scatter_reduce_kernel<T, Op, B200_MODE_DIRECT><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+                target, value, c.index, c.mask, c.n);
+            break;
+        case B200_MODE_NO_CONFLICTS:
+            scatter_reduce_kernel<T, Op, B200_MODE_NO_CONFLICTS><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+                target, value, c.index, c.mask, c.n);
+            break;
+        default:
+            scatter_reduce_kernel<T, Op, B200_MODE_LOCAL><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+                target, value, c.index, c.mask, c.n);
+            break;
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+typedef int (*ScatterFn)(const ScatterCall &);
+
+template <typename T> static ScatterFn pick_scatter_int(int op) {
+    switch (op) {
+        case B200_OP_ADD: return launch_scatter<T, B200_OP_ADD>;
+        case B200_OP_MIN: return launch_scatter<T, B200_OP_MIN>;
+        case B200_OP_MAX: return launch_scatter<T, B200_OP_MAX>;
+        case B200_OP_AND: return launch_scatter<T, B200_OP_AND>;
+        case B200_OP_OR:  return launch_scatter<T, B200_OP_OR>;
+        default: return nullptr;
+    }
+}
+
+template <typename T> static ScatterFn pick_scatter_float(int op) {
+    switch (op) {
+        case B200_OP_ADD: return launch_scatter<T, B200_OP_ADD>;
+        case B200_OP_MIN: return launch_scatter<T, B200_OP_MIN>;
+        case B200_OP_MAX: return launch_scatter<T, B200_OP_MAX>;
+        default: return nullptr;
+    }
+}
+
+static ScatterFn pick_scatter(int vt, int op) {
+    switch (vt) {
+        case B200_VT_INT32:   return pick_scatter_int<int32_t>(op);
+        case B200_VT_UINT32:  return pick_scatter_int<uint32_t>(op);
+        case B200_VT_INT64:   return pick_scatter_int<long long>(op);
+        case B200_VT_UINT64:  return pick_scatter_int<unsigned long long>(op);
+        case B200_VT_FLOAT16: return pick_scatter_float<__half>(op);
+        case B200_VT_FLOAT32: return pick_scatter_float<float>(op);
+        case B200_VT_FLOAT64: return pick_scatter_float<double>(op);
+        default: return nullptr;
+    }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_can_scatter_reduce(int vt, int op) {
+    // src/op.cpp:2735-2820 evaluated for the CUDA backend at compute capability 10.0
+    if (op == B200_OP_IDENTITY)
+        return 1;
+    return pick_scatter(vt, op) != nullptr;
+}
+
+int b200_scatter_reduce(void *stream_, int vt, int op, int mode, void *target,
+                        const void *value, const uint32_t *index, const uint8_t *mask,
+                        uint64_t n) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    ScatterFn fn = pick_scatter(vt, op);
+    if (!fn)
+        return fail(B200_ERR_UNSUPPORTED,
+                    "jit_var_scatter(): the %s backend does not support the requested type of "
+                    "atomic reduction (%s) for variables of type (%s)",
+                    "CUDA", op_name(op), type_name(vt));
+    if (mode == B200_MODE_AUTO)
+        mode = B200_MODE_LOCAL;
+    if (mode != B200_MODE_DIRECT && mode != B200_MODE_LOCAL && mode != B200_MODE_NO_CONFLICTS)
+        return fail(B200_ERR_UNSUPPORTED, "jit_var_scatter(): unsupported reduction mode %d", mode);
+    if (n == 0)
+        return B200_OK;
+    ScatterCall call{ resolve_stream(stream_), target, value, index, mask, n, mode };
+    return fn(call);
+}
+
+} // extern "C"

@@ -1,0 +1,206 @@
+/*
+ * include/drjit_b200.h -- C-ABI of the B200-native data-parallel primitive
+ * library that stands in for drjit-core's CUDA primitive path.
+ *
+ * This is the "tier 1" boundary: plain C, plain pointers and sizes, no C++ or
+ * torch types.  Every entry point names the reference interface it replaces
+ * (paths relative to the drjit-core tree).  The jit.h-signature layer that
+ * existing C++ callers link against sits on top of it in
+ * include/drjit_b200_jit.h.
+ *
+ * Conventions
+ *   - 'stream' is a cudaStream_t / CUstream passed as void*.  NULL selects the
+ *     library's own per-device stream (the reference keeps exactly one stream
+ *     per device, src/cuda_core.cpp:480), see b200_stream().
+ *   - All primitives are asynchronous on 'stream' unless stated otherwise;
+ *     temporaries come from the CUDA stream-ordered allocator.
+ *   - 'vt' / 'op' / 'mode' use the reference enum values: VarType
+ *     (include/drjit-core/jit.h:597-611), ReduceOp (:990-1014), ReduceMode
+ *     (:1017-1066).
+ *   - Return value 0 = success.  Non-zero: B200_ERR_* below; the message is
+ *     available from b200_last_error() (thread-local).  Argument errors are the
+ *     ones the reference raises as std::runtime_error.
+ *   - There is no CPU fallback: without a CUDA device every call fails with
+ *     B200_ERR_CUDA.
+ */
+#ifndef DRJIT_B200_H
+#define DRJIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#  define B200_API __declspec(dllexport)
+#else
+#  define B200_API __attribute__((visibility("default")))
+#endif
+
+enum {
+    B200_OK = 0,
+    B200_ERR_INVALID = 1,     /* reference: jitc_raise (bad size / block size) */
+    B200_ERR_UNSUPPORTED = 2, /* reference: "no existing kernel for type=.., op=.." */
+    B200_ERR_CUDA = 3,        /* reference: cuda_check -> jitc_fail */
+    B200_ERR_SYNC_FORBIDDEN = 4
+};
+
+/* VarType values used on this path (jit.h:597-611) */
+enum {
+    B200_VT_BOOL = 1, B200_VT_INT8 = 3, B200_VT_UINT8 = 4, B200_VT_INT16 = 5,
+    B200_VT_UINT16 = 6, B200_VT_INT32 = 7, B200_VT_UINT32 = 8, B200_VT_INT64 = 9,
+    B200_VT_UINT64 = 10, B200_VT_POINTER = 11, B200_VT_FLOAT16 = 13,
+    B200_VT_FLOAT32 = 14, B200_VT_FLOAT64 = 15
+};
+
+/* ReduceOp (jit.h:990-1014) */
+enum {
+    B200_OP_IDENTITY = 0, B200_OP_ADD = 1, B200_OP_MUL = 2, B200_OP_MIN = 3,
+    B200_OP_MAX = 4, B200_OP_AND = 5, B200_OP_OR = 6
+};
+
+/* ReduceMode (jit.h:1017-1066); Expand / Permute are compiler-level strategies
+ * with no kernel of their own and are rejected here. */
+enum {
+    B200_MODE_AUTO = 0, B200_MODE_DIRECT = 1, B200_MODE_LOCAL = 2,
+    B200_MODE_NO_CONFLICTS = 3
+};
+
+/* ---------------------------------------------------------------- runtime */
+
+/* Replaces jit_init(1 << CUDA) / jitc_cuda_init (src/cuda_core.cpp:266-539) for
+ * this path: enumerates devices, creates one stream per device, loads the
+ * sm_100a kernels linked into this library (instead of decompressing and
+ * JIT-compiling resources/kernels_75.lz4).  Idempotent. */
+B200_API int b200_init(void);
+B200_API int b200_shutdown(void);
+B200_API const char *b200_last_error(void);
+B200_API int b200_device_count(void);            /* jit_cuda_device_count, jit.h */
+B200_API int b200_set_device(int device);        /* jit_cuda_set_device, src/init.cpp:468-496 */
+B200_API int b200_device(void);
+B200_API void *b200_stream(void);                /* jit_cuda_stream, jit.h:192 */
+B200_API int b200_sync(void *stream);            /* jit_sync_thread, src/init.cpp:499+ */
+B200_API int b200_sm_count(void);
+
+/* jit_malloc / jit_free (src/malloc.cpp:102-306): kind 0 = device, 1 = pinned
+ * host.  Sizes are rounded like the reference (>= 64 B, next power of two,
+ * src/malloc.cpp:113-124) so code that relied on that padding keeps working. */
+B200_API void *b200_malloc(size_t size, int kind);
+B200_API int b200_free(void *ptr);
+B200_API int b200_memcpy(void *dst, const void *src, size_t size);                       /* jit_memcpy, jit.h:2202 */
+B200_API int b200_memcpy_async(void *stream, void *dst, const void *src, size_t size);   /* jit_memcpy_async, jit.h:2205 */
+
+/* jit_memset_async (jit.h:2199; CUDAThreadState::memset_async,
+ * src/cuda_ts.cpp:129-183 incl. the fill_64 kernel of resources/misc.cuh:28-32):
+ * writes 'size' elements of 'isize' in {1,2,4,8} bytes taken from host pointer
+ * 'src'. */
+B200_API int b200_memset_async(void *stream, void *ptr, uint64_t size, uint32_t isize,
+                               const void *src);
+
+/* jit_reduce_identity (jit.h:2840; src/var.cpp:2642-2652) */
+B200_API uint64_t b200_reduce_identity(int vt, int op);
+
+/* ------------------------------------------------------------- reductions */
+
+/* jit_block_reduce (jit.h:2239-2245) = CUDAThreadState::block_reduce
+ * (src/cuda_ts.cpp:195-352) + kernels resources/block_reduce.cuh.
+ * out[b] = op over in[b*block_size .. min((b+1)*block_size, size)).
+ * Errors: block_size == 0 or > size -> B200_ERR_INVALID; unsupported
+ * (type, op) -> B200_ERR_UNSUPPORTED; size == 0 is a no-op. */
+B200_API int b200_block_reduce(void *stream, int vt, int op, uint64_t size,
+                               uint64_t block_size, const void *in, void *out);
+
+/* jit_reduce (jit.h:2219-2221) == block_reduce with block_size == size
+ * (src/util.cpp:42-45) */
+B200_API int b200_reduce(void *stream, int vt, int op, const void *in, uint64_t size,
+                         void *out);
+
+/* jitc_reduce_dot (src/util.cpp:63-67) = CUDAThreadState::reduce_dot
+ * (src/cuda_ts.cpp:354-398) + resources/reduce_2.cuh.  f16 / f32 / f64. */
+B200_API int b200_reduce_dot(void *stream, int vt, const void *a, const void *b,
+                             uint64_t size, void *out);
+
+/* jitc_all / jitc_any (+ _async) (src/util.cpp:153-211,
+ * ThreadState::block_reduce_bool src/init.cpp:919-939).  'out' is a device or
+ * pinned byte.  Unlike the reference nothing is written past values[size). */
+B200_API int b200_all_async(void *stream, const uint8_t *values, uint64_t size, uint8_t *out);
+B200_API int b200_any_async(void *stream, const uint8_t *values, uint64_t size, uint8_t *out);
+B200_API int b200_all(void *stream, const uint8_t *values, uint64_t size, int *result);  /* synchronises */
+B200_API int b200_any(void *stream, const uint8_t *values, uint64_t size, int *result);  /* synchronises */
+
+/* ------------------------------------------------------------ prefix scans */
+
+/* jit_block_prefix_reduce (jit.h:2365-2373, positional order (size,
+ * block_size), src/util.cpp:55-61) = CUDAThreadState::block_prefix_reduce
+ * (src/cuda_ts.cpp:530-681) + resources/block_prefix_reduce.cuh.
+ * in == out is allowed. */
+B200_API int b200_block_prefix_reduce(void *stream, int vt, int op, uint64_t size,
+                                      uint64_t block_size, int exclusive, int reverse,
+                                      const void *in, void *out);
+
+/* Extension used by the multi-GPU front end and by > 2^32-element arrays:
+ * whole-array scan (one block) seeded with *carry_in (device scalar of the
+ * value type, may be NULL) and reporting the inclusive total of
+ * carry_in (+) array in *carry_out (device scalar, may be NULL). */
+B200_API int b200_prefix_reduce_carry(void *stream, int vt, int op, uint64_t size,
+                                      int exclusive, int reverse, const void *in,
+                                      void *out, const void *carry_in, void *carry_out);
+
+/* ---------------------------------------------------------------- compress */
+
+/* jit_compress (jit.h:2387) = CUDAThreadState::compress
+ * (src/cuda_ts.cpp:683-763) + resources/compress.cuh.  Synchronises the stream
+ * and returns the count through *count (host memory).  'in' is never written
+ * (the reference zero-fills its trailer). */
+B200_API int b200_compress(void *stream, const uint8_t *in, uint64_t size, uint32_t *out,
+                           uint32_t *count);
+/* Asynchronous form: *count_dev is device or pinned memory. */
+B200_API int b200_compress_async(void *stream, const uint8_t *in, uint64_t size,
+                                 uint32_t *out, uint32_t *count_dev);
+
+/* ------------------------------------------------------------------ mkperm */
+
+/* jit_block_mkperm (jit.h:2426-2432) = CUDAThreadState::block_mkperm
+ * (src/cuda_ts.cpp:788-975) + resources/mkperm.cuh.  'offsets' (may be NULL) is
+ * host-accessible memory of (4 * bucket_count + 1) u32 receiving
+ * (id, start, size, 0) records of the non-empty buckets -- in ascending id
+ * order, like the reference's CPU path (src/llvm_ts.cpp:871-887) -- and the
+ * unique count at [4 * bucket_count]; only when block_size == size.  The
+ * permutation is stable for every bucket count.  *unique receives the return
+ * value of the reference call.  Synchronises when offsets != NULL. */
+B200_API int b200_block_mkperm(void *stream, const uint32_t *values, uint32_t size,
+                               uint32_t block_size, uint32_t bucket_count,
+                               uint32_t *perm, uint32_t *offsets, uint32_t *unique);
+
+/* Phase 1 of the above on its own (per-bucket counts of the whole array into
+ * device memory hist[bucket_count]); the multi-GPU front end all-reduces it. */
+B200_API int b200_mkperm_histogram(void *stream, const uint32_t *values, uint64_t size,
+                                   uint32_t bucket_count, uint32_t *hist);
+
+/* ----------------------------------------------------------------- scatter */
+
+/* Stand-alone form of the scatter-reduce that the reference splices into fused
+ * JIT kernels (jitc_cuda_render_scatter_reduce, src/cuda_scatter.cpp:246-354;
+ * warp pre-reduction :125-244; op built by jitc_var_scatter src/op.cpp:2899-3086):
+ *   if (mask == NULL || mask[i]) target[index[i]] op= value[i],  i < n.
+ * op in {Add, Min, Max, And, Or}; legal (type, op) pairs as
+ * jitc_can_scatter_reduce (src/op.cpp:2735-2820).  mode: Auto -> Local (the
+ * reference's default flag set, jit.h:1766-1774). */
+B200_API int b200_scatter_reduce(void *stream, int vt, int op, int mode, void *target,
+                                 const void *value, const uint32_t *index,
+                                 const uint8_t *mask, uint64_t n);
+
+/* jit_can_scatter_reduce (jit.h:1123) for the CUDA backend on sm_100 */
+B200_API int b200_can_scatter_reduce(int vt, int op);
+
+/* --------------------------------------------------------------- telemetry */
+
+/* Number of kernels this library has launched since load (all threads). */
+B200_API uint64_t b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""GPU parity: atomic scatter-reduce through the C-ABI vs the CPU oracle.
+Integer results (and float min/max) are bit-exact; float adds are checked
+against the fp64-accumulated oracle with the tolerance stated below."""
+import numpy as np
+import pytest
+
+import oracle
+from cases import f32_input, fmix32, u32_input
+from util import empty_dev, rel_err, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+VT, OP = oracle.VT, oracle.OP
+MODES = {"auto": 0, "direct": 1, "local": 2}
+
+
+def index_input(n, m, kind):
+    i = np.arange(n, dtype=np.uint32)
+    if kind == "random":
+        return (fmix32(i) % np.uint32(m)).astype(np.uint32)
+    if kind == "coherent":  # runs of 64 equal indices (SURVEY.md 8d secondary set)
+        return ((i >> np.uint32(6)) % np.uint32(m)).astype(np.uint32)
+    if kind == "same":
+        return np.full(n, m // 2, dtype=np.uint32)
+    return ((i % np.uint32(3)) + (fmix32(i) % np.uint32(5) == 0) * (m - 3)).astype(np.uint32)  # few hot slots
+
+
+def run_scatter(dr, vt, op, target, value, index, mask, mode):
+    d_t = to_dev(target)
+    dr.scatter_reduce(vt, op, d_t, to_dev(value), to_dev(index),
+                      None if mask is None else to_dev(mask), index.size, mode=mode)
+    return to_host(d_t, target.dtype)
+
+
+@pytest.mark.parametrize("tname", ["u32", "i32", "u64", "i64"])
+def test_scatter_int(dr, O, tname):
+    dt = oracle.NP_OF_VT[VT[tname]]
+    bad = []
+    for n, m in ((1, 1), (1000, 7), (100003, 997), (1 << 20, 1 << 12)):
+        h = u32_input(n)
+        if tname[1:] == "32":
+            val = h.view(dt)
+        else:
+            val = ((h.astype(np.uint64) << np.uint64(20)) ^ h.astype(np.uint64)).view(dt)
+        mask = (fmix32(h) & np.uint32(3) != 0).astype(np.uint8)
+        for kind in ("random", "coherent", "same", "hot"):
+            idx = index_input(n, m, kind)
+            for opn in ("add", "min", "max", "and_", "or_"):
+                ident = O.reduce_identity(VT[tname], OP[opn])
+                if tname[1:] == "32":
+                    tgt = np.full(m, ident & 0xFFFFFFFF, dtype=np.uint32).view(dt)
+                else:
+                    tgt = np.full(m, ident, dtype=np.uint64).view(dt)
+                for mname, mode in MODES.items():
+                    for mk in (None, mask):
+                        got = run_scatter(dr, VT[tname], OP[opn], tgt, val, idx, mk, mode)
+                        ref = O.scatter_reduce(VT[tname], OP[opn], tgt, val, idx, mk)
+                        if not np.array_equal(got, ref):
+                            bad.append((n, m, kind, opn, mname, mk is not None))
+    assert not bad, bad[:20]
+
+
+# float add: the order of atomic additions is not defined, so compare against
+# the fp64-accumulated oracle: relative error <= 1e-5 (f32, all-positive values,
+# <= 2^8 addends per slot on average), 1e-12 (f64)
+@pytest.mark.parametrize("tname,tol", [("f32", 1e-5), ("f64", 1e-12)])
+def test_scatter_float(dr, O, tname, tol):
+    dt = oracle.NP_OF_VT[VT[tname]]
+    bad = []
+    for n, m in ((1000, 7), (1 << 20, 1 << 12), (100003, 997)):
+        val = f32_input(n).astype(dt)
+        sval = (val * 4 - 2).astype(dt)
+        for kind in ("random", "coherent", "hot"):
+            idx = index_input(n, m, kind)
+            for mname, mode in MODES.items():
+                got = run_scatter(dr, VT[tname], OP["add"], np.zeros(m, dtype=dt), val, idx, None, mode)
+                ref = O.scatter_reduce(VT[tname], OP["add"], np.zeros(m, dtype=dt), val, idx, wide=True)
+                sel = ref != 0
+                if rel_err(got[sel], ref[sel]) > tol or np.any(got[~sel] != 0):
+                    bad.append((n, m, kind, mname, rel_err(got[sel], ref[sel])))
+                for opn in ("min", "max"):  # emulated with integer atomics: exact
+                    ident = np.array([np.inf if opn == "min" else -np.inf], dtype=dt)[0]
+                    tgt = np.full(m, ident, dtype=dt)
+                    got = run_scatter(dr, VT[tname], OP[opn], tgt, sval, idx, None, mode)
+                    ref = O.scatter_reduce(VT[tname], OP[opn], tgt, sval, idx)
+                    if not np.array_equal(got, ref):
+                        bad.append((n, m, kind, mname, opn))
+    assert not bad, bad[:20]
+
+
+def test_scatter_f16(dr, O):
+    bad = []
+    n, m = 20000, 501
+    val = (f32_input(n) * 0.01).astype(np.float16)
+    for kind in ("random", "hot"):
+        idx = index_input(n, m, kind)
+        for mname, mode in MODES.items():
+            got = run_scatter(dr, VT["f16"], OP["add"], np.zeros(m, dtype=np.float16), val, idx, None, mode)
+            ref = O.scatter_reduce(VT["f16"], OP["add"], np.zeros(m, dtype=np.float16), val, idx, wide=True)
+            # every addition rounds to f16: allow count * ulp/2 accumulated error
+            cnt = np.bincount(idx, minlength=m)
+            tol = np.maximum(cnt, 1) * (2.0 ** -11) * np.maximum(ref.astype(np.float64), 1e-3)
+            if np.any(np.abs(got.astype(np.float64) - ref.astype(np.float64)) > tol):
+                bad.append((kind, mname, "add"))
+            for opn in ("min", "max"):
+                tgt = np.full(m, np.inf if opn == "min" else -np.inf, dtype=np.float16)
+                sval = (val * 100 - 1).astype(np.float16)
+                got = run_scatter(dr, VT["f16"], OP[opn], tgt, sval, idx, None, mode)
+                ref = O.scatter_reduce(VT["f16"], OP[opn], tgt, sval, idx)
+                if not np.array_equal(got, ref):
+                    bad.append((kind, mname, opn))
+    assert not bad, bad
+
+
+def test_scatter_reference_test_vector(dr):
+    # tests/mem.cpp:137-174 (10_scatter_atomic_rmw): 16 adds of 1.0 with duplicates
+    index = np.array([0, 0, 1, 2, 2, 2, 3, 4, 4, 4, 4, 0, 1, 2, 3, 4], dtype=np.uint32)
+    one = np.ones(16, dtype=np.float32)
+    got = run_scatter(dr, VT["f32"], OP["add"], np.zeros(5, dtype=np.float32), one, index, None, 0)
+    assert np.array_equal(got, np.bincount(index, minlength=5).astype(np.float32))
+    mask = (np.arange(16) % 2 == 0).astype(np.uint8)
+    got = run_scatter(dr, VT["f32"], OP["add"], np.zeros(5, dtype=np.float32), one, index, mask, 0)
+    assert np.array_equal(got, np.bincount(index[mask != 0], minlength=5).astype(np.float32))
+
+
+def test_scatter_no_conflicts_and_errors(dr, O):
+    n = 100000
+    idx = np.random.default_rng(3).permutation(n).astype(np.uint32)
+    val = u32_input(n)
+    tgt = fmix32(val)
+    got = run_scatter(dr, VT["u32"], OP["add"], tgt, val, idx, None, 3)
+    assert np.array_equal(got, O.scatter_reduce(VT["u32"], OP["add"], tgt, val, idx))
+    d = to_dev(val)
+    # src/op.cpp:2735-2820: no Mul, no And/Or on floats, no 8-bit types
+    assert not dr.jit_can_scatter_reduce(1, VT["u32"], OP["mul"])
+    assert not dr.jit_can_scatter_reduce(1, VT["f32"], OP["and_"])
+    assert not dr.jit_can_scatter_reduce(1, VT["u8"], OP["add"])
+    assert dr.jit_can_scatter_reduce(1, VT["f16"], OP["max"])
+    with pytest.raises(RuntimeError, match="does not support"):
+        dr.scatter_reduce(VT["u32"], OP["mul"], d, d, d, None, 10)
+    with pytest.raises(RuntimeError, match="does not support"):
+        dr.scatter_reduce(VT["f32"], OP["or_"], d, d, d, None, 10)
+
+
+def test_scatter_full_size(dr, O):
+    # BASELINE.json configs[4] (per device part): 2^26 -> 2^20 ScatterAdd
+    n, m = 1 << 26, 1 << 20
+    idx = (fmix32(np.arange(n, dtype=np.uint32)) & np.uint32(m - 1)).astype(np.uint32)
+    ival = u32_input(n)
+    got = run_scatter(dr, VT["u32"], OP["add"], np.zeros(m, dtype=np.uint32), ival, idx, None, 0)
+    assert np.array_equal(got, O.scatter_reduce(VT["u32"], OP["add"], np.zeros(m, dtype=np.uint32), ival, idx))
+    fval = f32_input(n)
+    got = run_scatter(dr, VT["f32"], OP["add"], np.zeros(m, dtype=np.float32), fval, idx, None, 1)
+    ref = O.scatter_reduce(VT["f32"], OP["add"], np.zeros(m, dtype=np.float32), fval, idx, wide=True)
+    assert rel_err(got, ref) <= 1e-5

@@ -1,0 +1,102 @@
+"""Quick per-primitive timing at the BASELINE.json sizes (development aid; the
+numbers that count come from bench.py)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import drjit_core_b200 as dr  # noqa: E402
+
+CUDA = 1
+F32, U32 = 14, 8
+ADD = 1
+PEAK = 6450.6
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(iters):
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        ts.append(s.elapsed_time(e))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    dr.jit_init()
+    res = {}
+    n = 1 << 28
+    x = torch.rand(n, device="cuda", dtype=torch.float32)
+    out = torch.empty(n, device="cuda", dtype=torch.float32)
+
+    def report(name, ms, nbytes):
+        res[name] = {"ms_med": ms[0], "ms_min": ms[1], "GBs": nbytes / ms[0] / 1e6,
+                     "frac": nbytes / ms[0] / 1e6 / PEAK}
+        print(f"{name:40s} {ms[0]:8.3f} ms  {nbytes / ms[0] / 1e6:8.1f} GB/s  {nbytes / ms[0] / 1e6 / PEAK:5.2f}", flush=True)
+
+    ms = timeit(lambda: out.copy_(x))
+    report("torch copy (r+w)", ms, 8 * n)
+    for bs in [1, 2, 4, 16, 128, 256, 1024, 4096, 1 << 16, 1 << 20, n]:
+        ms = timeit(lambda: dr.jit_block_reduce(CUDA, F32, ADD, n, bs, x, out))
+        report(f"block_reduce f32 bs={bs}", ms, 4 * n * (1 + 1 / bs))
+    for bs in [1, 2, 16, 128, 256, 1024, 4096, 1 << 16, n]:
+        ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 1, 0, x, out))
+        report(f"prefix f32 excl bs={bs}", ms, 8 * n if bs > 1 else 4 * n)
+    xi = x.view(torch.int32)
+    oi = out.view(torch.int32)
+    ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, U32, ADD, n, n, 1, 0, xi, oi))
+    report("prefix u32 excl bs=n", ms, 8 * n)
+    ms = timeit(lambda: dr.jit_reduce(CUDA, U32, ADD, xi, n, oi))
+    report("reduce u32", ms, 4 * n)
+    ms = timeit(lambda: dr.jit_reduce_dot(CUDA, F32, x, out, n, oi))
+    report("dot f32", ms, 8 * n)
+
+    for d in (0.01, 0.5, 0.99):
+        m = (torch.rand(n, device="cuda") < d).to(torch.uint8)
+        cnt = int(m.sum().item())
+        ms = timeit(lambda: dr.jit_compress(CUDA, m, n, oi))
+        report(f"compress d={d}", ms, n + 4 * cnt)
+        del m
+
+    n2 = 1 << 26
+    perm = torch.empty(n2, device="cuda", dtype=torch.int32)
+    for B in (16, 1024, 65536):
+        k = torch.randint(0, B, (n2,), device="cuda", dtype=torch.int32)
+        offs = torch.zeros(4 * B + 1, dtype=torch.int32).pin_memory()
+        ms = timeit(lambda: dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, offs), iters=5)
+        report(f"mkperm B={B}", ms, 8 * n2)
+        ms = timeit(lambda: dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, None), iters=5)
+        report(f"mkperm B={B} (no offsets)", ms, 8 * n2)
+        h = torch.empty(B, device="cuda", dtype=torch.int32)
+        ms = timeit(lambda: dr.mkperm_histogram(k, n2, B, h), iters=5)
+        report(f"histogram B={B}", ms, 4 * n2)
+
+    m2 = 1 << 20
+    idx = torch.randint(0, m2, (n2,), device="cuda", dtype=torch.int32)
+    val = torch.rand(n2, device="cuda")
+    tgt = torch.zeros(m2, device="cuda")
+    for mode, name in ((1, "direct"), (2, "local")):
+        ms = timeit(lambda: dr.scatter_reduce(F32, ADD, tgt, val, idx, None, n2, mode=mode), iters=5)
+        report(f"scatter_add f32 random {name}", ms, 8 * n2)
+    idx2 = (torch.arange(n2, device="cuda", dtype=torch.int32) >> 6) & (m2 - 1)
+    for mode, name in ((1, "direct"), (2, "local")):
+        ms = timeit(lambda: dr.scatter_reduce(F32, ADD, tgt, val, idx2, None, n2, mode=mode), iters=5)
+        report(f"scatter_add f32 coherent {name}", ms, 8 * n2)
+
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "perf_probe.json"), "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
