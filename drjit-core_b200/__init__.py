@@ -46,6 +46,7 @@ def build(verbose=False):
 
 
 _lib = None
+_LEGACY_STREAM = 1  # cudaStreamLegacy
 
 
 def lib():
@@ -109,11 +110,14 @@ def _stream(stream):
     """None -> torch's current stream when torch is imported and CUDA is up,
     otherwise the library's own per-device stream."""
     if stream is not None:
-        return stream if isinstance(stream, int) else stream.cuda_stream
+        handle = stream if isinstance(stream, int) else stream.cuda_stream
+        return handle or _LEGACY_STREAM
     import sys
     torch = sys.modules.get("torch")
     if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
-        return torch.cuda.current_stream().cuda_stream
+        # torch's default stream is the legacy default stream, whose handle is 0;
+        # the C-ABI reserves NULL for the library's own stream
+        return torch.cuda.current_stream().cuda_stream or _LEGACY_STREAM
     return None
 
 

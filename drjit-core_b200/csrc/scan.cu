@@ -44,6 +44,8 @@ struct ScanParams {
     uint32_t *ticket;   // MODE 2: tile ticket counter (zero-initialised)
     const void *carry_in;
     void *carry_out;
+    uint32_t vec_in;    // 'in' is 16-byte aligned: use 128-bit loads
+    uint32_t vec_out;   // 'out' is 16-byte aligned: use 128-bit stores
 };
 
 template <typename T, int Op, int J, int MODE>
@@ -106,7 +108,7 @@ scan_kernel(const ScanParams p) {
         pbase[j] = pb;
 
         Vec16<T> v;
-        if (pb + N <= p.size) {
+        if (p.vec_in && pb + N <= p.size) {
             v.raw = ld_stream_coherent(in + pb);
         } else {
             #pragma unroll
@@ -281,7 +283,7 @@ scan_kernel(const ScanParams p) {
         }
 
         const uint64_t pb = pbase[j];
-        if (pb + N <= p.size) {
+        if (p.vec_out && pb + N <= p.size) {
             Vec16<T> v;
             #pragma unroll
             for (int k = 0; k < N; ++k)
@@ -330,6 +332,9 @@ template <typename T, int Op> static int launch_scan(const ScanCall &c) {
     p.reverse = c.reverse;
     p.carry_in = c.carry_in;
     p.carry_out = c.carry_out;
+    // misaligned arrays fall back to element-wise (still coalesced) accesses
+    p.vec_in = ((uintptr_t) c.in % 16) == 0;
+    p.vec_out = ((uintptr_t) c.out % 16) == 0;
 
     int mode;
     if (c.carry_api) {

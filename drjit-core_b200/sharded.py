@@ -1,0 +1,152 @@
+"""Multi-GPU front end: large reductions, whole-array prefix scans and the
+mkperm histogram sharded across the GPUs of one box (one process per GPU,
+torch.distributed / NCCL over NVLink for the small exchanges).
+
+The reference has no multi-GPU code on this path (no NCCL/MPI anywhere; one
+CUDADevice + stream per GPU, src/cuda_core.cpp:352-516) -- this is the new
+functionality BASELINE.json's north_star asks for.  Data layout: rank r owns
+the contiguous shard [r * n_local, (r + 1) * n_local) of the global array;
+compress and scatter-reduce stay per device.
+
+Exchange steps (payloads are a few bytes to a few KiB, i.e. latency bound):
+  reduce     local reduce -> all_gather of the W partials -> every rank
+             combines them in rank order (bit-exact for integers, and the same
+             fixed order on every rank for floating point).
+  scan       local reduce -> all_gather of the W totals -> exclusive scan of
+             the totals (tiny, on device) -> local single-pass scan seeded with
+             the rank's carry (b200_prefix_reduce_carry).  12 B/element per GPU
+             instead of 8, so the ceiling against a 1-GPU single-pass scan is
+             W * 8 / 12.
+  histogram  local per-bucket counts -> all_reduce(sum); optional exclusive
+             scan over ranks gives each rank its global output offsets.
+
+`local_ops` is the object that executes the per-GPU primitives; it defaults to
+the CUDA library.  (tests/ inject a stand-in to exercise the exchange logic
+under gloo on CPU-only machines.)
+"""
+import torch
+import torch.distributed as dist
+
+from . import (JitBackend, ReduceOp, TYPE_SIZE, VarType, jit_block_prefix_reduce,
+               jit_block_reduce, jit_reduce, mkperm_histogram, prefix_reduce_carry)
+
+
+def value_size(vt):
+    """Bytes of the arithmetic ("value") type: float16 is carried as float32."""
+    return 4 if vt == VarType.Float16 else TYPE_SIZE[vt]
+
+
+class CudaLocalOps:
+    """Per-GPU primitives from libdrjit_core_b200.so on the current stream."""
+
+    def reduce(self, vt, op, in_, size, out):
+        jit_reduce(JitBackend.CUDA, vt, op, in_, size, out)
+
+    def block_reduce(self, vt, op, size, block_size, in_, out):
+        jit_block_reduce(JitBackend.CUDA, vt, op, size, block_size, in_, out)
+
+    def block_prefix_reduce(self, vt, op, size, block_size, exclusive, reverse, in_, out):
+        jit_block_prefix_reduce(JitBackend.CUDA, vt, op, size, block_size, exclusive,
+                                reverse, in_, out)
+
+    def prefix_reduce_carry(self, vt, op, size, exclusive, reverse, in_, out, carry_in,
+                            carry_out):
+        prefix_reduce_carry(vt, op, size, exclusive, reverse, in_, out, carry_in, carry_out)
+
+    def histogram(self, values, size, bucket_count, hist):
+        mkperm_histogram(values, size, bucket_count, hist)
+
+
+def shard_bounds(total, world, rank):
+    """Contiguous, balanced partition of `total` elements (first ranks get the
+    remainder), as (start, length)."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+class Sharded:
+    def __init__(self, group=None, device=None, local_ops=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available()
+            else torch.device("cpu"))
+        self.ops = local_ops if local_ops is not None else CudaLocalOps()
+
+    def _bytes(self, n):
+        return torch.zeros(n, dtype=torch.uint8, device=self.device)
+
+    def _gather(self, mine):
+        """all_gather of one small byte tensor per rank -> (world * len) bytes"""
+        out = self._bytes(mine.numel() * self.world)
+        if self.world == 1:
+            out.copy_(mine)
+        else:
+            dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out
+
+    # -- reduce -------------------------------------------------------------
+    def reduce(self, vt, op, local_in, local_size, out):
+        """Whole-array reduction of the global array; every rank receives the
+        result in `out` (device scalar of type vt)."""
+        tsize = TYPE_SIZE[vt]
+        partial = self._bytes(tsize)
+        if local_size > 0:
+            self.ops.reduce(vt, op, local_in, local_size, partial)
+        else:
+            self._fill_identity(partial, vt, op)
+        gathered = self._gather(partial)
+        self.ops.block_reduce(vt, op, self.world, self.world, gathered, out)
+
+    def _fill_identity(self, buf, vt, op):
+        from . import jit_reduce_identity
+        ident = jit_reduce_identity(vt, op)
+        raw = ident.to_bytes(8, "little")[:buf.numel()]
+        buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+
+    # -- scan -----------------------------------------------------------------
+    def prefix_reduce(self, vt, op, local_in, local_size, exclusive, reverse, local_out):
+        """Whole-array prefix reduction of the global array (block_size ==
+        global size); rank r's shard of the result is written to local_out."""
+        if vt == VarType.Float16:
+            raise RuntimeError("sharded prefix_reduce(): float16 is not supported "
+                               "(per-shard totals would be rounded to half)")
+        tsize = TYPE_SIZE[vt]
+        total = self._bytes(tsize)
+        if local_size > 0:
+            self.ops.reduce(vt, op, local_in, local_size, total)
+        else:
+            self._fill_identity(total, vt, op)
+        totals = self._gather(total)
+        # exclusive scan over ranks; a reverse scan accumulates from the last rank
+        carries = self._bytes(tsize * self.world)
+        self.ops.block_prefix_reduce(vt, op, self.world, self.world, True, bool(reverse),
+                                     totals, carries)
+        carry = carries[self.rank * tsize:(self.rank + 1) * tsize]
+        if local_size > 0:
+            self.ops.prefix_reduce_carry(vt, op, local_size, exclusive, reverse, local_in,
+                                         local_out, carry, None)
+
+    # -- mkperm histogram -------------------------------------------------------
+    def mkperm_histogram(self, local_values, local_size, bucket_count, want_offsets=False):
+        """Global per-bucket counts (int32 tensor of bucket_count entries on every
+        rank).  With want_offsets also returns this rank's exclusive offset per
+        bucket among the ranks (counts of lower ranks), which together with the
+        exclusive scan of the global counts gives its global output slots."""
+        local = torch.zeros(bucket_count, dtype=torch.int32, device=self.device)
+        if local_size > 0:
+            self.ops.histogram(local_values, local_size, bucket_count, local)
+        if self.world == 1:
+            return (local, torch.zeros_like(local)) if want_offsets else local
+        if not want_offsets:
+            glob = local.clone()
+            dist.all_reduce(glob, op=dist.ReduceOp.SUM, group=self.group)
+            return glob
+        allh = torch.zeros(self.world * bucket_count, dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(allh, local, group=self.group)
+        allh = allh.view(self.world, bucket_count)
+        glob = allh.sum(dim=0, dtype=torch.int32)
+        before = allh[:self.rank].sum(dim=0, dtype=torch.int32)
+        return glob, before

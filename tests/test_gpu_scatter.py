@@ -60,8 +60,10 @@ def test_scatter_int(dr, O, tname):
 
 
 # float add: the order of atomic additions is not defined, so compare against
-# the fp64-accumulated oracle: relative error <= 1e-5 (f32, all-positive values,
-# <= 2^8 addends per slot on average), 1e-12 (f64)
+# the fp64-accumulated oracle.  Per slot with c addends (all positive):
+# relative error <= tol * max(1, sqrt(c / 4096)), tol = 1e-5 (f32) / 1e-12 (f64)
+# -- a slot that serially accumulates hundreds of thousands of addends (the
+# "hot" pattern) legitimately drifts by a few 1e-5.
 @pytest.mark.parametrize("tname,tol", [("f32", 1e-5), ("f64", 1e-12)])
 def test_scatter_float(dr, O, tname, tol):
     dt = oracle.NP_OF_VT[VT[tname]]
@@ -75,8 +77,11 @@ def test_scatter_float(dr, O, tname, tol):
                 got = run_scatter(dr, VT[tname], OP["add"], np.zeros(m, dtype=dt), val, idx, None, mode)
                 ref = O.scatter_reduce(VT[tname], OP["add"], np.zeros(m, dtype=dt), val, idx, wide=True)
                 sel = ref != 0
-                if rel_err(got[sel], ref[sel]) > tol or np.any(got[~sel] != 0):
-                    bad.append((n, m, kind, mname, rel_err(got[sel], ref[sel])))
+                cnt = np.bincount(idx, minlength=m)[sel]
+                slot_tol = tol * np.maximum(1.0, np.sqrt(cnt / 4096.0))
+                err = np.abs(got[sel].astype(np.float64) - ref[sel]) / np.abs(ref[sel].astype(np.float64))
+                if np.any(err > slot_tol) or np.any(got[~sel] != 0):
+                    bad.append((n, m, kind, mname, float(err.max())))
                 for opn in ("min", "max"):  # emulated with integer atomics: exact
                     ident = np.array([np.inf if opn == "min" else -np.inf], dtype=dt)[0]
                     tgt = np.full(m, ident, dtype=dt)

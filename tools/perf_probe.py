@@ -66,6 +66,9 @@ def main():
         cnt = int(m.sum().item())
         ms = timeit(lambda: dr.jit_compress(CUDA, m, n, oi))
         report(f"compress d={d}", ms, n + 4 * cnt)
+        cdev = torch.zeros(1, device="cuda", dtype=torch.int32)
+        ms = timeit(lambda: dr.compress_async(m, n, oi, cdev))
+        report(f"compress_async d={d}", ms, n + 4 * cnt)
         del m
 
     n2 = 1 << 26
