@@ -98,12 +98,6 @@ static int prepare_device(int dev) {
                     dev, d.cc_major, d.cc_minor);
     B200_CUDA_CHECK(cudaSetDevice(dev));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-    // keep freed temporaries cached in the pool (jitc_malloc caches as well)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t threshold = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
     return B200_OK;
 }
 
@@ -123,10 +117,30 @@ int sm_count() {
     return 148;
 }
 
+// Freed temporaries must stay cached in the device's default pool: with the
+// default release threshold (0) every synchronisation hands them back to the
+// driver and the next cudaMallocAsync costs milliseconds.  Done once per device,
+// for whichever device / stream the caller uses (jitc_malloc caches as well).
+static std::atomic<bool> g_pool_ready[64];
+
+static void retain_pool(int dev) {
+    if (dev < 0 || dev >= 64 || g_pool_ready[dev].load(std::memory_order_acquire))
+        return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    } else {
+        cudaGetLastError();
+    }
+    g_pool_ready[dev].store(true, std::memory_order_release);
+}
+
 void *temp_alloc(size_t bytes, cudaStream_t stream) {
     void *ptr = nullptr;
     if (bytes == 0)
         bytes = 16;
+    retain_pool(current_device());
     if (cudaMallocAsync(&ptr, bytes, stream) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
