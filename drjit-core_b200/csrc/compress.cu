@@ -2,7 +2,7 @@
 //
 // Replaces CUDAThreadState::compress (src/cuda_ts.cpp:683-763) and
 // resources/compress.cuh (compress_small / compress_large_init /
-// compress_large).  One kernel for every size:
+// compress_large).  Masks of up to 32768 entries use one single-pass kernel:
 //   - 256 threads x J 16-byte vectors = 16 KiB of mask per tile (the reference:
 //     2 KiB), tiles handed out by an atomic ticket and chained with decoupled
 //     look-back on 64-bit {status, count} descriptors;
@@ -12,8 +12,12 @@
 //   - indices are compacted per warp row in shared memory and written with
 //     contiguous (coalesced) stores instead of one predicated scattered store
 //     per mask byte (compress.cuh:146-149).
+// Larger masks take the bit-packed two-pass path further down.
 #include "common.cuh"
 
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -168,6 +172,228 @@ compress_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint
 }
 
 
+// --------------------------------------------------- bit-packed two-pass path
+//
+// Large masks.  A single-pass compaction chained by look-back is limited by the
+// rate at which tiles can be chained (measured ~90 tiles/us with scan_fast.cu's
+// machinery, i.e. 1.5 TB/s of mask for 16 KiB tiles), and 4 bytes of staging per
+// mask byte cap the tile size.  Packing the mask to one BIT per entry first makes
+// a second pass cheap instead: 1 + 1/8 + 1/8 + 4 d bytes per entry against the
+// algorithmic 1 + 4 d, with three simple, fully parallel kernels:
+//   pack    16 mask bytes per thread -> 16 bits; 32-bit words of the bit mask and
+//           one count per 8192-entry tile                          (HBM: n + n/8)
+//   offsets exclusive scan of the tile counts by one CTA          (L2-resident)
+//   expand  one bit-mask word per thread, ranks by popcount + block scan, index
+//           run of the tile compacted in shared memory and written with
+//           contiguous stores                                  (HBM: n/8 + 4 count)
+// Only bit 0 of a mask byte is looked at (entries are required to be 0 or 1,
+// jit.h:2377-2379).
+
+static constexpr int CP_THREADS = 256;
+static constexpr uint32_t CP_TILE = 8192;                  // entries per expand tile
+static constexpr uint32_t CP_WORDS = CP_TILE / 32;         // 256 words = one per thread
+
+/// bit k of the result = bit 0 of byte k of w (k < 4)
+B200_DEVICE uint32_t pack4(uint32_t w) {
+    return (((w & 0x01010101u) * 0x00204081u) >> 21) & 0xfu;
+}
+
+B200_DEVICE uint32_t pack16(uint4 v) {
+    return pack4(v.x) | (pack4(v.y) << 4) | (pack4(v.z) << 8) | (pack4(v.w) << 12);
+}
+
+/// Virtual layout: entry i of the mask is byte (i + mis) of the 16-byte aligned
+/// array (in - mis); bits / tiles are indexed in that virtual space.  A CTA packs
+/// two tiles (16384 virtual bytes): warp w, step s covers the 1024 bytes starting
+/// at ((2 * blockIdx.x * 8 + s * 8 + w) * 1024).
+__global__ void __launch_bounds__(CP_THREADS)
+compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis,
+                     uint32_t *__restrict__ bits, uint32_t *__restrict__ counts,
+                     uint32_t ntiles) {
+    __shared__ uint32_t s_cnt[2][CP_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *vin = in - mis;
+    const uint64_t vend = size + mis; // valid virtual bytes: [mis, vend)
+
+    uint4 v[2][2];
+    #pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const uint64_t chunk = ((uint64_t) blockIdx.x * 2 + s) * 8 + warp; // 1024-byte chunk
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint64_t vb = chunk * 1024 + (uint64_t) r * 512 + lane * 16;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (vb >= mis && vb + 16 <= vend) {
+                x = ld_stream(vin + vb);
+            } else if (vb < vend && vb + 16 > mis) {
+                uint32_t w[4] = { 0, 0, 0, 0 };
+                #pragma unroll
+                for (int b = 0; b < 16; ++b)
+                    if (vb + b >= mis && vb + b < vend)
+                        w[b >> 2] |= (uint32_t) vin[vb + b] << (8 * (b & 3));
+                x = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            v[s][r] = x;
+        }
+    }
+    #pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const uint64_t chunk = ((uint64_t) blockIdx.x * 2 + s) * 8 + warp;
+        const uint32_t b0 = pack16(v[s][0]), b1 = pack16(v[s][1]);
+        // even lanes assemble the word of row 0, odd lanes the word of row 1
+        const uint32_t got = __shfl_xor_sync(FULL_MASK, (lane & 1) ? b0 : b1, 1);
+        const uint32_t word = (lane & 1) ? (got | (b1 << 16)) : (b0 | (got << 16));
+        const uint64_t widx = chunk * 32 + (lane & 1) * 16 + (lane >> 1);
+        if (widx * 32 < vend)
+            bits[widx] = word;
+        const uint32_t c = __reduce_add_sync(FULL_MASK, __popc(word));
+        if (lane == 0)
+            s_cnt[s][warp] = c;
+    }
+    __syncthreads();
+    if (tid < 2) {
+        uint32_t c = 0;
+        #pragma unroll
+        for (int w = 0; w < CP_THREADS / 32; ++w)
+            c += s_cnt[tid][w];
+        const uint32_t tile = blockIdx.x * 2 + tid;
+        if (tile < ntiles)
+            counts[tile] = c;
+    }
+}
+
+/// In-place exclusive scan of the tile counts by one CTA; total -> *count_out.
+__global__ void __launch_bounds__(1024)
+compress_offsets_kernel(uint32_t *__restrict__ counts, uint32_t ntiles,
+                        uint32_t *__restrict__ count_out) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += 4096) {
+        const uint32_t i = base + tid * 4;
+        uint32_t c[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k)
+            c[k] = i + k < ntiles ? counts[i + k] : 0;
+        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        uint32_t incl = mine;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= (uint32_t) d)
+                incl += up;
+        }
+        if (lane == 31)
+            s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wsum = s_warp[lane], wincl = wsum;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t up = __shfl_up_sync(FULL_MASK, wincl, d);
+            if (lane >= (uint32_t) d)
+                wincl += up;
+        }
+        const uint32_t carry = s_carry;
+        uint32_t run = carry + __shfl_sync(FULL_MASK, wincl - wsum, warp) + incl - mine;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < ntiles)
+                counts[i + k] = run;
+            run += c[k];
+        }
+        __syncthreads();
+        if (tid == 1023)
+            s_carry = run;
+        __syncthreads();
+    }
+    if (tid == 0)
+        *count_out = s_carry;
+}
+
+/// One tile of 8192 entries per CTA: word per thread -> ranks -> staged index
+/// run -> contiguous stores to out[offsets[tile] ...).
+__global__ void __launch_bounds__(CP_THREADS)
+compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ offsets,
+                       uint32_t mis, uint32_t *__restrict__ out) {
+    extern __shared__ uint32_t cp_stage[]; // CP_TILE indices
+    __shared__ uint32_t s_warp[CP_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t word = __ldg(bits + (uint64_t) tile * CP_WORDS + tid);
+    const uint32_t cnt = __popc(word);
+    uint32_t incl = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= (uint32_t) d)
+            incl += up;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    #pragma unroll
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+        const uint32_t t = s_warp[w];
+        before += (uint32_t) w < warp ? t : 0;
+        total += t;
+    }
+    if (total == 0)
+        return; // CTA-uniform
+    uint32_t o = before + incl - cnt;
+    const uint32_t item0 = tile * CP_TILE + tid * 32 - mis;
+    uint32_t rest = word;
+    while (rest) {
+        const uint32_t b = __ffs(rest) - 1;
+        rest &= rest - 1;
+        cp_stage[o++] = item0 + b;
+    }
+    __syncthreads();
+    uint32_t *dst = out + offsets[tile];
+    for (uint32_t i = tid; i < total; i += CP_THREADS)
+        dst[i] = cp_stage[i];
+}
+
+static int compress_two_pass(cudaStream_t stream, const uint8_t *in, uint64_t size, uint32_t *out,
+                             uint32_t *count_dev) {
+    const uint32_t mis = (uint32_t) ((uintptr_t) in & 15);
+    const uint64_t vsize = size + mis;
+    const uint32_t ntiles = (uint32_t) ceil_div(vsize, CP_TILE);
+    const uint64_t nwords = (uint64_t) ntiles * CP_WORDS;
+    const size_t bytes = (size_t) (nwords + ntiles) * sizeof(uint32_t);
+    uint32_t *bits = (uint32_t *) temp_alloc(bytes, stream);
+    if (!bits)
+        return fail(B200_ERR_CUDA, "jit_compress(): out of memory (%zu bytes)", bytes);
+    uint32_t *counts = bits + nwords;
+    // words past the end of the mask are never written by the pack kernel
+    const uint64_t last_word = ceil_div(vsize, 32);
+    if (nwords > last_word) {
+        cudaError_t err = cudaMemsetAsync(bits + last_word, 0, (nwords - last_word) * 4, stream);
+        if (err != cudaSuccess) {
+            temp_free(bits, stream);
+            return cuda_fail(err, "cudaMemsetAsync");
+        }
+    }
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev].load(std::memory_order_relaxed)) {
+        cudaFuncSetAttribute(compress_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) (CP_TILE * 4));
+        attr_set[dev].store(true, std::memory_order_relaxed);
+    }
+    compress_pack_kernel<<<(ntiles + 1) / 2, CP_THREADS, 0, stream>>>(in, size, mis, bits, counts, ntiles);
+    compress_offsets_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, count_dev);
+    compress_expand_kernel<<<ntiles, CP_THREADS, CP_TILE * 4, stream>>>(bits, counts, mis, out);
+    count_launch(2);
+    temp_free(bits, stream);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 } // namespace b200
 
 using namespace b200;
@@ -186,6 +412,11 @@ int b200_compress_async(void *stream_, const uint8_t *in, uint64_t size, uint32_
     }
     if (size > 0xffffffffull)
         return fail(B200_ERR_INVALID, "jit_compress(): array too large (indices are 32 bit)!");
+    // small masks: one launch of the single-pass kernel; large ones: two passes
+    // over a bit-packed copy of the mask
+    if (size > 32768)
+        return compress_two_pass(stream, in, size, out, count_dev);
+
     constexpr int J = 4;
     constexpr uint32_t TILE = COMPRESS_THREADS * J * 16;
     uint32_t mis = (uint32_t) ((uintptr_t) in & 15);

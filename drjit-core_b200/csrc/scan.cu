@@ -22,7 +22,7 @@
 //     decoupled look-back over 64-bit {status, value} descriptors.  A tile
 //     that contains a segment head publishes its aggregate directly as an
 //     inclusive prefix, which is also what stops look-back at block borders.
-#include "common.cuh"
+#include "scan.cuh"
 
 namespace b200 {
 
@@ -300,18 +300,6 @@ scan_kernel(const ScanParams p) {
 
 // ---------------------------------------------------------------- dispatch
 
-struct ScanCall {
-    cudaStream_t stream;
-    const void *in;
-    void *out;
-    uint64_t size;
-    uint64_t bs;       // == size for whole-array scans
-    bool exclusive, reverse;
-    const void *carry_in;
-    void *carry_out;
-    bool carry_api;    // whole array is one segment, optional carry
-};
-
 template <typename T, int Op> static int launch_scan(const ScanCall &c) {
     using V = typename ValueOf<T>::type;
     constexpr int N = VecInfo<T>::N;
@@ -450,6 +438,10 @@ int b200_block_prefix_reduce(void *stream_, int vt, int op, uint64_t size,
     }
     ScanCall call{ stream, in, out, size, block_size, exclusive != 0, reverse != 0,
                    nullptr, nullptr, false };
+    bool handled = false;
+    rc = scan_fast_dispatch(vt, op, call, &handled);
+    if (rc || handled)
+        return rc;
     return fn(call);
 }
 
@@ -479,6 +471,10 @@ int b200_prefix_reduce_carry(void *stream_, int vt, int op, uint64_t size, int e
     }
     ScanCall call{ stream, in, out, size, size, exclusive != 0, reverse != 0, carry_in,
                    carry_out, true };
+    bool handled = false;
+    rc = scan_fast_dispatch(vt, op, call, &handled);
+    if (rc || handled)
+        return rc;
     return fn(call);
 }
 

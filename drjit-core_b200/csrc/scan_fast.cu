@@ -1,0 +1,763 @@
+// scan_fast.cu -- streaming prefix reductions: the fast paths of
+// jit_block_prefix_reduce (include/drjit-core/jit.h:2365-2373).
+//
+// Replaces the kernel of resources/block_prefix_reduce.cuh (one element per
+// thread, Hillis-Steele in shared memory with two barriers per round, look-back
+// only between the 1024-element chunks of one block) for the two shapes that
+// matter at scale:
+//
+//   POW2   block_size is a power of two and at most one tile: blocks never
+//          cross a tile, so tiles are independent.
+//   CHAIN  the whole array is one block (optionally seeded with a carry), or
+//          block_size is a power-of-two multiple of the tile: tiles are chained
+//          with decoupled look-back over 64-bit {status, value} descriptors.
+//   In both modes tiles are handed out by an atomic ticket: every predecessor
+//   of a tile is therefore owned by a CTA that is already running (forward
+//   progress of the look-back), and fast SMs take more tiles (load balance).
+//
+// Everything else (odd block sizes, pointers that are not 16-byte aligned) is
+// served by the general segmented kernel in scan.cu.
+//
+// Kernel structure (persistent CTAs, 512 compute threads):
+//   - a tile is 512 * J 16-byte vectors (32 KiB for J = 4).  Thread 0 keeps a
+//     ring of S shared-memory slots filled with 1-D bulk copies (the TMA engine,
+//     cp.async.bulk + mbarrier complete_tx) S - 2 tiles ahead of the tile being
+//     computed, so loads stay in flight while the CTA computes;
+//   - CHAIN only: two helper warps run ahead of the compute warps on the tiles
+//     that have landed in the ring.  One reduces the tile and publishes its
+//     aggregate immediately, the other resolves the tile's exclusive prefix by
+//     look-back and hands it over through an mbarrier, so neither the look-back
+//     latency nor a neighbour waiting for this CTA's aggregate stalls the
+//     stream;
+//   - warp w owns the contiguous rows [w * J, (w + 1) * J) of 32 vectors; a
+//     thread scans its vector in registers, rows are scanned with shuffles
+//     (only log2(lanes per block) steps for small blocks), row and warp totals
+//     are combined through registers / one shared-memory exchange;
+//   - results are written back into the slot and leave with one bulk store per
+//     tile (cp.async.bulk.global.shared::cta), which also drains asynchronously.
+//   The last, partial tile of an array uses guarded 128-bit loads / stores.
+#include "scan.cuh"
+#include "pipeline.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+
+namespace b200 {
+
+template <int X> struct CLog2 { static constexpr int value = X <= 1 ? 0 : 1 + CLog2<X / 2>::value; };
+
+struct FastParams {
+    const void *in;
+    void *out;
+    uint64_t size;       // elements
+    uint32_t ntiles;
+    uint32_t log2_bs;    // POW2: log2(block_size)
+    uint32_t seg_mask;   // CHAIN: tiles per block - 1 (0xffffffff: one block)
+    uint32_t tile_off;   // CHAIN: phase of the block grid in logical tile space
+    uint32_t exclusive;
+    uint32_t reverse;
+    uint32_t debug;      // development switches
+    uint64_t *desc;      // CHAIN: ntiles descriptors (zero-initialised)
+    uint32_t *ticket;    // tile ticket counter (zero-initialised)
+    const void *carry_in;
+    void *carry_out;
+};
+
+#if defined(B200_SCAN_TUNING)
+// development counters (accumulated in registers, flushed once per warp):
+// [0] look-back steps, [1] polls, [2] cycles in look-back, [3] compute cycles
+// waiting for a prefix, [4] compute cycles waiting for a tile to land, [5] tiles,
+// [6] aggregate-warp cycles waiting for a tile, [7] look-back cycles waiting for
+// the aggregate, [8] aggregate-warp cycles reducing, [9] thread-0 cycles in
+// issue(), [10] compute-loop cycles in total (thread 32), [11] thread-0 cycles
+// waiting for the aggregate warp before a refill
+__device__ unsigned long long g_scan_dbg[16];
+#define DBG_DECL() unsigned long long dbg_acc[16] = { 0 }
+#define DBG_ADD(i, v) dbg_acc[i] += (unsigned long long) (v)
+#define DBG_ADD_LANE0(i, v) DBG_ADD(i, v)
+#define DBG_FLUSH() do { if (p.debug & 2) { for (int i_ = 0; i_ < 16; ++i_) if (dbg_acc[i_]) atomicAdd(&g_scan_dbg[i_], dbg_acc[i_]); } } while (0)
+#define DBG_CLOCK() clock64()
+#else
+#define DBG_DECL() ((void) 0)
+#define DBG_ADD(i, v) ((void) 0)
+#define DBG_ADD_LANE0(i, v) ((void) 0)
+#define DBG_FLUSH() ((void) 0)
+#define DBG_CLOCK() 0ll
+#endif
+
+/// Barrier among the THREADS compute threads only (the look-back warp of the
+/// CHAIN kernel never joins it)
+template <int THREADS> B200_DEVICE void compute_sync() {
+    asm volatile("bar.sync 1, %0;" :: "n"(THREADS) : "memory");
+}
+
+/// Scan of one tile held in registers.  On entry e[j][k] holds the tile's values
+/// in logical order (warp-contiguous rows); on exit e[j][k] is the inclusive
+/// prefix inside the vector and carry[j] the exclusive prefix of the vector
+/// within its block *inside this tile*.  FULL: the tile is one run (no block
+/// boundaries).
+template <typename T, int Op, int J, int THREADS, bool FULL> struct TileScan {
+    using V = typename ValueOf<T>::type;
+    using R = Red<V, Op>;
+    static constexpr int N = VecInfo<T>::N;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int LOG2_N = CLog2<N>::value;
+    static constexpr int LOG2_J = CLog2<J>::value;
+    static constexpr int LOG2_W = CLog2<WARPS>::value;
+
+    static B200_DEVICE void run(V (&e)[J][N], V (&carry)[J], uint32_t log2_bs, uint32_t lane,
+                                uint32_t warp, V *s_warp) {
+        // ---- inside the vector
+        const uint32_t mask = FULL ? 0xffffffffu : ((1u << log2_bs) - 1u);
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            #pragma unroll
+            for (int k = 1; k < N; ++k)
+                if (FULL || (k & mask))
+                    e[j][k] = R::apply(e[j][k - 1], e[j][k]);
+        }
+
+        // ---- inside a row: blocks of L lanes
+        uint32_t L = 32;
+        if (!FULL) {
+            L = (1u << log2_bs) >> LOG2_N;
+            L = L < 1 ? 1 : (L > 32 ? 32 : L);
+        }
+        const uint32_t sl = lane & (L - 1);
+        V a[J];
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            a[j] = e[j][N - 1];
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            if (FULL || (uint32_t) d < L) {
+                #pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    V up = shfl_up(a[j], d);
+                    if (sl >= (uint32_t) d)
+                        a[j] = R::apply(up, a[j]);
+                }
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            V up = shfl_up(a[j], 1);
+            carry[j] = sl ? up : R::identity();
+        }
+
+        // ---- across the rows of a warp, then across warps
+        if (FULL || log2_bs > (uint32_t) (LOG2_N + 5)) {
+            uint32_t rows = J;
+            if (!FULL) {
+                uint32_t lr = log2_bs - (LOG2_N + 5);
+                rows = lr >= (uint32_t) LOG2_J ? J : (1u << lr);
+            }
+            V run = R::identity();
+            #pragma unroll
+            for (int j = 0; j < J; ++j) {
+                V rt = shfl_idx(a[j], 31);
+                if (!FULL && (j & (rows - 1)) == 0)
+                    run = R::identity();
+                carry[j] = R::apply(run, carry[j]);
+                run = R::apply(run, rt);
+            }
+
+            if (FULL || log2_bs > (uint32_t) (LOG2_N + 5 + LOG2_J)) {
+                uint32_t warps = WARPS;
+                if (!FULL) {
+                    uint32_t lw = log2_bs - (LOG2_N + 5 + LOG2_J);
+                    warps = lw >= (uint32_t) LOG2_W ? WARPS : (1u << lw);
+                }
+                if (lane == 0)
+                    s_warp[warp] = run;
+                compute_sync<THREADS>();
+                const uint32_t first = warp & ~(warps - 1);
+                V wc = R::identity();
+                #pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    V t = s_warp[w];
+                    if ((uint32_t) w >= first && (uint32_t) w < warp)
+                        wc = R::apply(wc, t);
+                }
+                #pragma unroll
+                for (int j = 0; j < J; ++j)
+                    carry[j] = R::apply(wc, carry[j]);
+            }
+        }
+    }
+};
+
+/// THREADS compute threads (+ one look-back warp when CHAIN), tiles of
+/// THREADS * J vectors, ring of S shared-memory slots.
+template <typename T, int Op, int J, int S, int THREADS, bool CHAIN, int LB>
+__global__ void __launch_bounds__(THREADS + (CHAIN ? 32 + 32 * LB : 0), THREADS >= 512 ? 2 : 1)
+scan_stream_kernel(const FastParams p) {
+    using V = typename ValueOf<T>::type;
+    using R = Red<V, Op>;
+    constexpr int N = VecInfo<T>::N;
+    constexpr int WARPS = THREADS / 32;
+    constexpr uint32_t VECS = THREADS * J;
+    constexpr uint32_t TILE = VECS * N;
+    constexpr uint32_t TILE_BYTES = VECS * 16;
+    constexpr uint32_t NONE = 0xffffffffu;
+    static_assert(LB <= S, "every look-back warp must meet one of the S trailing empty slots");
+
+    extern __shared__ __align__(128) uint8_t sf_smem[];
+    uint4 *slots = (uint4 *) sf_smem; // S * VECS vectors
+    __shared__ __align__(8) uint64_t s_full[S];  // bulk load of the slot has landed
+    // CHAIN: hand-over between aggregate warp -> look-back warps -> compute warps.
+    // These rings have 2 * S entries (tile k uses entry k % M): a slot is handed
+    // back to the producer as soon as the compute warps hold the tile in
+    // registers, i.e. possibly before the look-back of that tile has started.
+    constexpr int M = 2 * S;
+    __shared__ __align__(8) uint64_t s_agg[M];   // s_total / s_mtile entry is valid
+    __shared__ __align__(8) uint64_t s_pref[M];  // s_prefix entry is valid
+    __shared__ uint32_t s_tile[S];
+    __shared__ uint32_t s_mtile[M];
+    __shared__ V s_total[M];
+    __shared__ V s_prefix[M];
+    __shared__ V s_warp[WARPS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T *in = (const T *) p.in;
+    T *out = (T *) p.out;
+    DBG_DECL();
+
+    // ---- producer side (thread 0): tile assignment + bulk loads into the ring
+    // Tiles are handed out by an atomic ticket in both modes.  CHAIN needs it
+    // for forward progress; POW2 for load balance (measured: with a static
+    // round-robin assignment the slowest SM is busy 23 % longer than the
+    // fastest one and the kernel loses 13 %).
+    auto issue = [&](uint32_t slot, uint32_t t) {
+        if (t >= p.ntiles) {
+            s_tile[slot] = NONE;
+            mbar_arrive(&s_full[slot]);
+            return;
+        }
+        s_tile[slot] = t;
+        const uint32_t pt = p.reverse ? p.ntiles - 1 - t : t;
+        const uint64_t base = (uint64_t) pt * TILE;
+        if (base + TILE <= p.size) {
+            mbar_arrive_expect_tx(&s_full[slot], TILE_BYTES);
+            bulk_g2s(slots + (size_t) slot * VECS, in + base, TILE_BYTES, &s_full[slot]);
+        } else {
+            mbar_arrive(&s_full[slot]); // partial tile: loaded directly by its readers
+        }
+    };
+
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < S; ++s)
+            mbar_init(&s_full[s], 1);
+        #pragma unroll
+        for (int s = 0; s < M; ++s) {
+            mbar_init(&s_agg[s], 1);
+            mbar_init(&s_pref[s], 1);
+        }
+        mbar_fence_init();
+        for (uint32_t i = 0; i < (uint32_t) S; ++i)
+            issue(i, atomicAdd(p.ticket, 1u));
+    }
+    __syncthreads();
+
+    if constexpr (CHAIN) {
+        // ---- two helper warps run ahead of the compute warps.
+        // Aggregate warp: reduces every tile as soon as it has landed and
+        // publishes the aggregate at once -- never held up by a look-back, so
+        // that the successors of a tile find its aggregate without waiting for
+        // this CTA.
+        if (warp == WARPS) {
+            int none_seen = 0;
+            for (uint32_t k = 0;; ++k) {
+                const uint32_t slot = k % S;
+                long long c0 = DBG_CLOCK();
+                mbar_wait(&s_full[slot], (k / S) & 1);
+                long long c1 = DBG_CLOCK();
+                DBG_ADD(6, c1 - c0);
+                const uint32_t tile = s_tile[slot];
+                const uint32_t m = k % M;
+                if (tile == NONE) {
+                    // wake every look-back warp: the next LB slots are NONE too
+                    if (lane == 0) {
+                        s_mtile[m] = NONE;
+                        mbar_arrive(&s_agg[m]);
+                    }
+                    if (++none_seen == LB)
+                        break;
+                    continue;
+                }
+                (void) c1;
+                const uint32_t ptile = p.reverse ? p.ntiles - 1 - tile : tile;
+                const uint64_t base = (uint64_t) ptile * TILE;
+                const uint4 *slot_ptr = slots + (size_t) slot * VECS;
+                constexpr int AU = 8; // vectors in flight per lane
+                static_assert(VECS % (32 * AU) == 0, "tile must be a multiple of 256 vectors");
+                V acc[AU];
+                #pragma unroll
+                for (int u = 0; u < AU; ++u)
+                    acc[u] = R::identity();
+                if (base + TILE <= p.size) {
+                    #pragma unroll 1
+                    for (uint32_t i = lane; i < VECS; i += 32 * AU) {
+                        Vec16<T> v[AU];
+                        #pragma unroll
+                        for (int u = 0; u < AU; ++u)
+                            v[u].raw = slot_ptr[i + u * 32];
+                        #pragma unroll
+                        for (int u = 0; u < AU; ++u) {
+                            // pairwise inside the vector: short dependency chains
+                            V t[N];
+                            #pragma unroll
+                            for (int kk = 0; kk < N; ++kk)
+                                t[kk] = to_value<T>(v[u].elem[kk]);
+                            #pragma unroll
+                            for (int w = N / 2; w > 0; w >>= 1) {
+                                #pragma unroll
+                                for (int kk = 0; kk < w; ++kk)
+                                    t[kk] = R::apply(t[kk], t[kk + w]);
+                            }
+                            acc[u] = R::apply(acc[u], t[0]);
+                        }
+                    }
+                } else {
+                    for (uint64_t i = base + lane; i < p.size; i += 32)
+                        acc[0] = R::apply(acc[0], to_value<T>(in[i]));
+                }
+                #pragma unroll
+                for (int w = AU / 2; w > 0; w >>= 1) {
+                    #pragma unroll
+                    for (int u = 0; u < w; ++u)
+                        acc[u] = R::apply(acc[u], acc[u + w]);
+                }
+                const V total = warp_reduce<V, Op>(acc[0]);
+                if (lane == 0) {
+                    const bool first = ((tile + p.tile_off) & p.seg_mask) == 0;
+                    if (first) {
+                        V P = R::identity();
+                        if (p.carry_in)
+                            P = *(const V *) p.carry_in;
+                        Desc<V>::publish(p.desc, tile, DESC_PREFIX, R::apply(P, total));
+                    } else {
+                        Desc<V>::publish(p.desc, tile, DESC_AGGREGATE, total);
+                    }
+                    s_mtile[m] = tile;
+                    s_total[m] = total;
+                    mbar_arrive(&s_agg[m]);
+                    DBG_ADD(8, DBG_CLOCK() - c1);
+                }
+                __syncwarp();
+            }
+            if (lane == 0)
+                DBG_FLUSH();
+            return;
+        }
+        // Look-back warps (LB of them, taking the CTA's tiles in turn): resolve
+        // the exclusive prefix of a tile by decoupled look-back over windows of
+        // 32 descriptors, publish the inclusive prefix and hand the exclusive
+        // one to the compute warps.
+        if (warp > WARPS) {
+            for (uint32_t k = warp - (WARPS + 1);; k += LB) {
+                const uint32_t m = k % M;
+                long long c0 = DBG_CLOCK();
+                mbar_wait(&s_agg[m], (k / M) & 1);
+                const uint32_t tile = s_mtile[m];
+                if (tile == NONE)
+                    break;
+                long long c1 = DBG_CLOCK();
+                DBG_ADD(7, c1 - c0);
+                DBG_ADD(5, 1);
+                const V total = s_total[m];
+                const bool first = ((tile + p.tile_off) & p.seg_mask) == 0;
+                V P = R::identity();
+                if (first) {
+                    if (p.carry_in)
+                        P = *(const V *) p.carry_in;
+                } else {
+                    int64_t win = (int64_t) tile - 1;
+                    while (true) {
+                        // window of the 32 preceding tiles; lane 0 is the nearest.
+                        // A poll is one L2 round trip (~0.9 us under streaming load)
+                        // and polling competes with the stream for L2 bandwidth, so
+                        // only lanes whose entry is still INVALID poll again, after
+                        // a short back-off; entries beyond the nearest PREFIX are
+                        // not needed at all.
+                        const int64_t idx = win - lane;
+                        V val = R::identity();
+                        uint32_t st = DESC_PREFIX, pre;
+                        if (idx >= 0)
+                            st = Desc<V>::observe(p.desc, (uint32_t) idx, val);
+                        DBG_ADD_LANE0(0, 1);
+                        DBG_ADD_LANE0(1, 1);
+                        while (true) {
+                            pre = __ballot_sync(FULL_MASK, st == DESC_PREFIX);
+                            uint32_t inv = __ballot_sync(FULL_MASK, st == DESC_INVALID);
+                            if (pre)
+                                inv &= (1u << (__ffs(pre) - 1)) - 1u;
+                            if (!inv)
+                                break;
+                            __nanosleep(100);
+                            if (st == DESC_INVALID)
+                                st = Desc<V>::observe(p.desc, (uint32_t) idx, val);
+                            DBG_ADD_LANE0(1, 1);
+                        }
+                        if (pre) {
+                            const uint32_t stop = __ffs(pre) - 1;
+                            V contrib = lane <= stop ? val : R::identity();
+                            P = R::apply(warp_reduce<V, Op>(contrib), P);
+                            break;
+                        }
+                        P = R::apply(warp_reduce<V, Op>(val), P);
+                        win -= 32;
+                    }
+                    if (lane == 0)
+                        Desc<V>::publish(p.desc, tile, DESC_PREFIX, R::apply(P, total));
+                }
+                if (lane == 0) {
+                    s_prefix[m] = P;
+                    if (p.carry_out && tile == p.ntiles - 1)
+                        *(V *) p.carry_out = R::apply(P, total);
+                    mbar_arrive(&s_pref[m]);
+                    DBG_ADD(2, DBG_CLOCK() - c1);
+                }
+                __syncwarp();
+            }
+            if (lane == 0)
+                DBG_FLUSH();
+            return;
+        }
+    }
+
+    // ---- compute warps
+    long long loop0 = DBG_CLOCK();
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t slot = k % S;
+        const uint32_t parity = (k / S) & 1;
+        // ticket of the tile that will refill this slot: requested now, needed
+        // only after the tile has been read (hides the atomic's round trip)
+        uint32_t next_ticket = 0;
+        if (tid == 0)
+            next_ticket = atomicAdd(p.ticket, 1u);
+        long long w0 = DBG_CLOCK();
+        mbar_wait(&s_full[slot], parity);
+        if (tid == 32)
+            DBG_ADD(4, DBG_CLOCK() - w0);
+        const uint32_t tile = s_tile[slot];
+        if (tile == NONE)
+            break;
+        const uint32_t ptile = p.reverse ? p.ntiles - 1 - tile : tile;
+        const uint64_t base = (uint64_t) ptile * TILE;
+        const bool bulk = base + TILE <= p.size; // CTA-uniform
+        const uint4 *slot_ptr = slots + (size_t) slot * VECS;
+
+        // ---- load (logical vector lvi of the tile <-> physical vector pvi)
+        V e[J][N];
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const uint32_t lvi = warp * (J * 32) + j * 32 + lane;
+            const uint32_t pvi = p.reverse ? VECS - 1 - lvi : lvi;
+            const uint64_t pb = base + (uint64_t) pvi * N;
+            if (bulk || pb + N <= p.size) {
+                Vec16<T> v;
+                if (bulk)
+                    v.raw = slot_ptr[pvi];
+                else
+                    v.raw = ld_stream_coherent(in + pb);
+                if (p.reverse) {
+                    #pragma unroll
+                    for (int kk = 0; kk < N; ++kk)
+                        e[j][kk] = to_value<T>(v.elem[N - 1 - kk]);
+                } else {
+                    #pragma unroll
+                    for (int kk = 0; kk < N; ++kk)
+                        e[j][kk] = to_value<T>(v.elem[kk]);
+                }
+            } else {
+                #pragma unroll
+                for (int kk = 0; kk < N; ++kk) {
+                    const uint64_t pi = pb + (p.reverse ? N - 1 - kk : kk);
+                    e[j][kk] = pi < p.size ? to_value<T>(in[pi]) : R::identity();
+                }
+            }
+        }
+
+        // ---- the tile now lives in registers (and the helper warps are done
+        // with it: they run ahead): hand the slot back to the producer, which
+        // refills it with the tile S steps ahead
+        compute_sync<THREADS>();
+        if (tid == 0) {
+            long long i0 = DBG_CLOCK();
+            if constexpr (CHAIN)
+                mbar_wait(&s_agg[k % M], (k / M) & 1); // the aggregate warp has read the slot
+            long long i1 = DBG_CLOCK();
+            issue(slot, next_ticket);
+            DBG_ADD(11, i1 - i0);
+            DBG_ADD(9, DBG_CLOCK() - i1);
+        }
+
+        // ---- tile-local scan
+        V carry[J];
+        TileScan<T, Op, J, THREADS, CHAIN>::run(e, carry, p.log2_bs, lane, warp, s_warp);
+
+        // ---- prefix of the tile (resolved ahead of time by the look-back warps)
+        if constexpr (CHAIN) {
+            long long w1 = DBG_CLOCK();
+            mbar_wait(&s_pref[k % M], (k / M) & 1);
+            if (tid == 32)
+                DBG_ADD(3, DBG_CLOCK() - w1);
+            const V P = s_prefix[k % M];
+            #pragma unroll
+            for (int j = 0; j < J; ++j)
+                carry[j] = R::apply(P, carry[j]);
+        }
+
+        // ---- results: 128-bit streaming stores straight from registers
+        if (p.debug & 1)
+            compute_sync<THREADS>();
+        const uint32_t mask = CHAIN ? 0xffffffffu : ((1u << p.log2_bs) - 1u);
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const uint32_t lvi = warp * (J * 32) + j * 32 + lane;
+            const uint32_t pvi = p.reverse ? VECS - 1 - lvi : lvi;
+            const uint64_t pb = base + (uint64_t) pvi * N;
+            V res[N];
+            if (p.exclusive) {
+                res[0] = carry[j];
+                #pragma unroll
+                for (int kk = 1; kk < N; ++kk)
+                    res[kk] = (kk & mask) ? R::apply(carry[j], e[j][kk - 1]) : R::identity();
+            } else {
+                #pragma unroll
+                for (int kk = 0; kk < N; ++kk)
+                    res[kk] = R::apply(carry[j], e[j][kk]);
+            }
+            if (bulk || pb + N <= p.size) {
+                Vec16<T> v;
+                if (p.reverse) {
+                    #pragma unroll
+                    for (int kk = 0; kk < N; ++kk)
+                        v.elem[N - 1 - kk] = from_value<T>(res[kk]);
+                } else {
+                    #pragma unroll
+                    for (int kk = 0; kk < N; ++kk)
+                        v.elem[kk] = from_value<T>(res[kk]);
+                }
+                if (p.debug & 4)
+                    *(uint4 *) (out + pb) = v.raw;
+                else
+                    st_stream(out + pb, v.raw);
+            } else {
+                #pragma unroll
+                for (int kk = 0; kk < N; ++kk) {
+                    const uint64_t pi = pb + (p.reverse ? N - 1 - kk : kk);
+                    if (pi < p.size)
+                        out[pi] = from_value<T>(res[kk]);
+                }
+            }
+        }
+    }
+    if (tid == 32)
+        DBG_ADD(10, DBG_CLOCK() - loop0);
+    if (tid == 0 || tid == 32)
+        DBG_FLUSH();
+}
+
+// ---------------------------------------------------------------- dispatch
+
+/// 0: general kernel only, otherwise (default) the streaming kernels.
+/// Development switch.
+static int scan_path() {
+    static int path = -1;
+    if (path < 0) {
+        const char *s = getenv("B200_SCAN_PATH");
+        path = s ? atoi(s) : 2;
+    }
+    return path;
+}
+
+template <typename K> static int prepare_kernel(K kernel, int threads, size_t smem, int *occupancy) {
+    if (smem > 48 * 1024)
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int) smem));
+    int occ = 0;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    *occupancy = occ < 1 ? 1 : occ;
+    if (getenv("B200_DEBUG"))
+        fprintf(stderr, "b200: scan_stream_kernel: %d threads, %d CTAs/SM, %zu B dynamic smem\n",
+                threads, occ, smem);
+    return B200_OK;
+}
+
+// Tile geometry: THREADS compute threads x J vectors per tile, S ring slots, LB
+// look-back warps.  Default 512 x 4 = 32 KiB tiles, 3 slots, two CTAs per SM:
+// measured on B200 at 2^28 fp32, POW2 0.318 ms (6.7 TB/s) and CHAIN 0.38 ms
+// (5.6 TB/s).  256 x 4 with 6 slots: POW2 the same, CHAIN 0.44 ms; a second
+// look-back warp makes CHAIN slower (more polling, same dependency latency).
+template <int THREADS_, int J_, int S_, int LB_ = 2> struct Geom {
+    static constexpr int THREADS = THREADS_, J = J_, S = S_, LB = LB_;
+};
+using DefaultGeom = Geom<512, 4, 3, 1>;
+
+template <typename T, int Op, bool CHAIN, typename G>
+static int launch_stream(const ScanCall &c, FastParams &p) {
+    using V = typename ValueOf<T>::type;
+    constexpr size_t SMEM = (size_t) G::S * G::THREADS * G::J * 16;
+    constexpr int BLOCK = G::THREADS + (CHAIN ? 32 + 32 * G::LB : 0);
+    auto kernel = scan_stream_kernel<T, Op, G::J, G::S, G::THREADS, CHAIN, CHAIN ? G::LB : 0>;
+
+    // per device: opt in to the dynamic shared memory size, query residency
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = dev < 64 ? occ_cache[dev].load(std::memory_order_relaxed) : 0;
+    if (occ == 0) {
+        int rc = prepare_kernel(kernel, BLOCK, SMEM, &occ);
+        if (rc)
+            return rc;
+        if (dev < 64)
+            occ_cache[dev].store(occ, std::memory_order_relaxed);
+    }
+
+    void *scratch = nullptr;
+    {
+        size_t desc_bytes = CHAIN ? (size_t) p.ntiles * Desc<V>::WORDS * sizeof(uint64_t) : 0;
+        scratch = temp_alloc(desc_bytes + 16, c.stream);
+        if (!scratch)
+            return fail(B200_ERR_CUDA, "jit_block_prefix_reduce(): out of memory");
+        B200_CUDA_CHECK(cudaMemsetAsync(scratch, 0, desc_bytes + 16, c.stream));
+        p.desc = (uint64_t *) scratch;
+        p.ticket = (uint32_t *) ((uint8_t *) scratch + desc_bytes);
+    }
+    uint32_t grid = (uint32_t) std::min<uint64_t>(p.ntiles, (uint64_t) sm_count() * occ);
+    kernel<<<grid, BLOCK, SMEM, c.stream>>>(p);
+    if (scratch)
+        temp_free(scratch, c.stream);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <typename T, int Op, typename G> static int launch_fast_g(const ScanCall &c, bool *handled) {
+    constexpr int N = VecInfo<T>::N;
+    constexpr uint32_t TILE = G::THREADS * G::J * N;
+    *handled = false;
+    if (scan_path() == 0 || (((uintptr_t) c.in | (uintptr_t) c.out) & 15) != 0)
+        return B200_OK;
+    if (c.size >= 0xffffffffull - 2 * TILE)
+        return B200_OK;
+
+    FastParams p{};
+    p.in = c.in;
+    p.out = c.out;
+    p.size = c.size;
+    p.ntiles = (uint32_t) ceil_div(c.size, TILE);
+    p.exclusive = c.exclusive;
+    p.reverse = c.reverse;
+    p.carry_in = c.carry_in;
+    p.carry_out = c.carry_out;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char *e = getenv("B200_SCAN_DBG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.debug = (uint32_t) dbg;
+    }
+
+    bool chain;
+    if (c.carry_api || c.bs >= c.size) {
+        chain = true;
+        p.seg_mask = 0xffffffffu;
+    } else if (is_pow2(c.bs) && c.bs <= TILE) {
+        chain = false;
+        p.log2_bs = log2i(c.bs);
+    } else if (is_pow2(c.bs)) {
+        chain = true;
+        uint32_t tps = (uint32_t) (c.bs / TILE);
+        p.seg_mask = tps - 1;
+        p.tile_off = c.reverse ? (tps - p.ntiles % tps) % tps : 0;
+    } else {
+        return B200_OK;
+    }
+    *handled = true;
+    if (chain)
+        return launch_stream<T, Op, true, G>(c, p);
+    return launch_stream<T, Op, false, G>(c, p);
+}
+
+template <typename T, int Op> static int launch_fast(const ScanCall &c, bool *handled) {
+#if defined(B200_SCAN_TUNING)
+    // development build: alternative geometries for fp32 Add, picked at run time
+    if constexpr (std::is_same<T, float>::value && Op == B200_OP_ADD) {
+        static int geom = -1;
+        if (geom < 0) {
+            const char *s = getenv("B200_SCAN_GEOM");
+            geom = s ? atoi(s) : 0;
+        }
+        switch (geom) {
+            case 1: return launch_fast_g<T, Op, Geom<256, 4, 6, 1>>(c, handled);
+            case 2: return launch_fast_g<T, Op, Geom<512, 4, 3, 2>>(c, handled);
+            case 3: return launch_fast_g<T, Op, Geom<512, 4, 3, 1>>(c, handled);
+            case 4: return launch_fast_g<T, Op, Geom<512, 2, 6, 2>>(c, handled);
+            case 5: return launch_fast_g<T, Op, Geom<256, 4, 4, 1>>(c, handled);
+            case 6: return launch_fast_g<T, Op, Geom<384, 4, 4, 2>>(c, handled);
+            case 7: return launch_fast_g<T, Op, Geom<384, 4, 4, 1>>(c, handled);
+            default: break;
+        }
+    }
+#endif
+    return launch_fast_g<T, Op, DefaultGeom>(c, handled);
+}
+
+typedef int (*FastFn)(const ScanCall &, bool *);
+
+template <typename T, bool Bits> static FastFn pick_fast_op(int op) {
+    switch (op) {
+        case B200_OP_ADD: return launch_fast<T, B200_OP_ADD>;
+        case B200_OP_MUL: return launch_fast<T, B200_OP_MUL>;
+        case B200_OP_MIN: return launch_fast<T, B200_OP_MIN>;
+        case B200_OP_MAX: return launch_fast<T, B200_OP_MAX>;
+        case B200_OP_AND: if constexpr (Bits) return launch_fast<T, B200_OP_AND>; else return nullptr;
+        case B200_OP_OR:  if constexpr (Bits) return launch_fast<T, B200_OP_OR>; else return nullptr;
+        default: return nullptr;
+    }
+}
+
+template <typename T> static FastFn pick_fast_minmax(int op) {
+    switch (op) {
+        case B200_OP_MIN: return launch_fast<T, B200_OP_MIN>;
+        case B200_OP_MAX: return launch_fast<T, B200_OP_MAX>;
+        default: return nullptr;
+    }
+}
+
+int scan_fast_dispatch(int vt, int op, const ScanCall &call, bool *handled) {
+    const bool minmax = op == B200_OP_MIN || op == B200_OP_MAX;
+    FastFn fn = nullptr;
+    switch (vt) {
+        case B200_VT_INT32:  fn = minmax ? pick_fast_minmax<int32_t>(op) : pick_fast_op<uint32_t, true>(op); break;
+        case B200_VT_UINT32: fn = pick_fast_op<uint32_t, true>(op); break;
+        case B200_VT_INT64:  fn = minmax ? pick_fast_minmax<int64_t>(op) : pick_fast_op<uint64_t, true>(op); break;
+        case B200_VT_UINT64: fn = pick_fast_op<uint64_t, true>(op); break;
+        case B200_VT_FLOAT16: fn = pick_fast_op<__half, false>(op); break;
+        case B200_VT_FLOAT32: fn = pick_fast_op<float, false>(op); break;
+        case B200_VT_FLOAT64: fn = pick_fast_op<double, false>(op); break;
+        default: break;
+    }
+    *handled = false;
+    if (!fn)
+        return B200_OK;
+    return fn(call, handled);
+}
+
+#if defined(B200_SCAN_TUNING)
+extern "C" __attribute__((visibility("default"))) void b200_scan_debug(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_scan_dbg, sizeof(g_scan_dbg));
+    if (reset) {
+        unsigned long long zero[16] = { 0 };
+        cudaMemcpyToSymbol(g_scan_dbg, zero, sizeof(zero));
+    }
+}
+#endif
+
+} // namespace b200

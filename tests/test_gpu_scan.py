@@ -176,3 +176,53 @@ def test_full_size_scan(dr, O):
         got = to_host(out, np.float32)
         sums = xf.reshape(-1, bs).astype(np.float64).sum(axis=1)
         assert rel_err(got.reshape(-1, bs)[:, -1], sums) <= 1e-5
+
+
+@pytest.mark.parametrize("tname", ["u32", "i32", "u64", "i64"])
+def test_prefix_streaming_paths(dr, O, tname):
+    """The persistent bulk-copy kernels of scan_fast.cu: sizes beyond one wave of
+    CTAs (several tiles per CTA), power-of-two blocks inside a tile (POW2), whole
+    arrays and tile-multiple power-of-two blocks (CHAIN), ragged tails, reverse,
+    in place.  Integer results are bit-exact."""
+    bad = []
+    sizes = [(1 << 22) + 12345, 3 * (1 << 20), 2500001]
+    for size in sizes:
+        x = int_input(tname, size)
+        for bs in (2, 4, 8, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 1 << 16, 1 << 20, size):
+            for opn, excl, rev in (("add", 0, 0), ("add", 1, 1), ("max", 1, 0), ("min", 0, 1)):
+                got = run_scan(dr, VT[tname], OP[opn], x, bs, excl, rev, inplace=(bs == 64))
+                ref = O.block_prefix_reduce(VT[tname], OP[opn], x, bs, excl, rev)
+                if not np.array_equal(got, ref):
+                    bad.append((size, bs, opn, excl, rev))
+    assert not bad, bad
+
+
+def test_prefix_streaming_float_types(dr, O):
+    # f32 / f64 / f16 through the streaming kernels; tolerances as in test_prefix_float
+    bad = []
+    size = (1 << 21) + 77
+    for tname, tol in (("f32", 1e-5), ("f64", 1e-12)):
+        dt = oracle.NP_OF_VT[VT[tname]]
+        x = f32_input(size).astype(dt)
+        for bs in (2, 16, 128, 1024, 4096, 1 << 15, size):
+            for excl, rev in ((0, 0), (1, 0), (1, 1)):
+                got = run_scan(dr, VT[tname], OP["add"], x, bs, excl, rev)
+                ref = O.block_prefix_reduce(VT[tname], OP["add"], x, bs, excl, rev, wide=True)
+                sel = ref != 0
+                err = rel_err(got[sel], ref[sel])
+                if err > tol or not np.all(got[~sel] == 0):
+                    bad.append((tname, bs, excl, rev, err))
+            got = run_scan(dr, VT[tname], OP["min"], x, bs, 0, 1)
+            if not np.array_equal(got, O.block_prefix_reduce(VT[tname], OP["min"], x, bs, 0, 1)):
+                bad.append((tname, bs, "min"))
+    x = (f32_input(1 << 18) * 0.01).astype(np.float16)
+    for bs in (8, 256, 8192):
+        got = run_scan(dr, VT["f16"], OP["add"], x, bs, 0, 0).astype(np.float64)
+        ref = O.block_prefix_reduce(VT["f16"], OP["add"], x, bs, 0, 0, wide=True).astype(np.float64)
+        sel = ref != 0
+        if rel_err(got[sel], ref[sel]) > 2.0 ** -10:
+            bad.append(("f16", bs, rel_err(got[sel], ref[sel])))
+        got = run_scan(dr, VT["f16"], OP["max"], x, bs, 0, 0)
+        if not np.array_equal(got, O.block_prefix_reduce(VT["f16"], OP["max"], x, bs, 0, 0)):
+            bad.append(("f16", bs, "max"))
+    assert not bad, bad

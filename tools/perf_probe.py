@@ -33,6 +33,11 @@ def timeit(fn, iters=10, warmup=3):
 
 
 def main():
+    want = set(sys.argv[1:])
+
+    def on(name):
+        return not want or name in want
+
     dr.jit_init()
     res = {}
     n = 1 << 28
@@ -46,22 +51,30 @@ def main():
 
     ms = timeit(lambda: out.copy_(x))
     report("torch copy (r+w)", ms, 8 * n)
-    for bs in [1, 2, 4, 16, 128, 256, 1024, 4096, 1 << 16, 1 << 20, n]:
+    for bs in [1, 2, 4, 16, 128, 256, 1024, 4096, 1 << 16, 1 << 20, n] if on("reduce") else []:
         ms = timeit(lambda: dr.jit_block_reduce(CUDA, F32, ADD, n, bs, x, out))
         report(f"block_reduce f32 bs={bs}", ms, 4 * n * (1 + 1 / bs))
-    for bs in [1, 2, 16, 128, 256, 1024, 4096, 1 << 16, n]:
+    for bs in [1, 2, 16, 128, 256, 1024, 4096, 8192, 1 << 16, n] if on("scan") else []:
         ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 1, 0, x, out))
         report(f"prefix f32 excl bs={bs}", ms, 8 * n if bs > 1 else 4 * n)
     xi = x.view(torch.int32)
     oi = out.view(torch.int32)
-    ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, U32, ADD, n, n, 1, 0, xi, oi))
-    report("prefix u32 excl bs=n", ms, 8 * n)
-    ms = timeit(lambda: dr.jit_reduce(CUDA, U32, ADD, xi, n, oi))
-    report("reduce u32", ms, 4 * n)
-    ms = timeit(lambda: dr.jit_reduce_dot(CUDA, F32, x, out, n, oi))
-    report("dot f32", ms, 8 * n)
+    if on("scan"):
+        ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, U32, ADD, n, n, 1, 0, xi, oi))
+        report("prefix u32 excl bs=n", ms, 8 * n)
+        ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, U32, ADD, n, n, 0, 1, xi, oi))
+        report("prefix u32 incl reverse bs=n", ms, 8 * n)
+        x64 = x.view(torch.int64)
+        o64 = out.view(torch.int64)
+        ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, 10, ADD, n // 2, n // 2, 1, 0, x64, o64))
+        report("prefix u64 excl bs=n (2^27)", ms, 8 * n)
+    if on("reduce"):
+        ms = timeit(lambda: dr.jit_reduce(CUDA, U32, ADD, xi, n, oi))
+        report("reduce u32", ms, 4 * n)
+        ms = timeit(lambda: dr.jit_reduce_dot(CUDA, F32, x, out, n, oi))
+        report("dot f32", ms, 8 * n)
 
-    for d in (0.01, 0.5, 0.99):
+    for d in (0.01, 0.5, 0.99) if on("compress") else []:
         m = (torch.rand(n, device="cuda") < d).to(torch.uint8)
         cnt = int(m.sum().item())
         ms = timeit(lambda: dr.jit_compress(CUDA, m, n, oi))
@@ -73,7 +86,7 @@ def main():
 
     n2 = 1 << 26
     perm = torch.empty(n2, device="cuda", dtype=torch.int32)
-    for B in (16, 1024, 65536):
+    for B in (16, 1024, 65536) if on("mkperm") else []:
         k = torch.randint(0, B, (n2,), device="cuda", dtype=torch.int32)
         offs = torch.zeros(4 * B + 1, dtype=torch.int32).pin_memory()
         ms = timeit(lambda: dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, offs), iters=5)
@@ -84,6 +97,8 @@ def main():
         ms = timeit(lambda: dr.mkperm_histogram(k, n2, B, h), iters=5)
         report(f"histogram B={B}", ms, 4 * n2)
 
+    if not on("scatter"):
+        return
     m2 = 1 << 20
     idx = torch.randint(0, m2, (n2,), device="cuda", dtype=torch.int32)
     val = torch.rand(n2, device="cuda")
