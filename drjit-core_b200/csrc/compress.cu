@@ -183,9 +183,9 @@ compress_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint
 //   pack    16 mask bytes per thread -> 16 bits; 32-bit words of the bit mask and
 //           one count per 8192-entry tile                          (HBM: n + n/8)
 //   offsets exclusive scan of the tile counts by one CTA          (L2-resident)
-//   expand  one bit-mask word per thread, ranks by popcount + block scan, index
-//           run of the tile compacted in shared memory and written with
-//           contiguous stores                                  (HBM: n/8 + 4 count)
+//   expand  one bit-mask word per thread, ranks by popcount + block scan; a warp
+//           walks its non-empty words and stores every word's index run with
+//           one contiguous store instruction                  (HBM: n/8 + 4 count)
 // Only bit 0 of a mask byte is looked at (entries are required to be 0 or 1,
 // jit.h:2377-2379).
 
@@ -313,12 +313,15 @@ compress_offsets_kernel(uint32_t *__restrict__ counts, uint32_t ntiles,
         *count_out = s_carry;
 }
 
-/// One tile of 8192 entries per CTA: word per thread -> ranks -> staged index
-/// run -> contiguous stores to out[offsets[tile] ...).
+/// One tile of 8192 entries per CTA, one bit-mask word per thread.  After the
+/// block-wide exclusive scan of the popcounts a warp walks its non-empty words:
+/// the word and its output offset are broadcast, lane j owns bit j and stores the
+/// index at offset + (number of set bits below j).  Set bits of a word land on
+/// consecutive addresses, so every store instruction writes one contiguous run
+/// (no shared-memory staging, no bank conflicts).
 __global__ void __launch_bounds__(CP_THREADS)
 compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ offsets,
                        uint32_t mis, uint32_t *__restrict__ out) {
-    extern __shared__ uint32_t cp_stage[]; // CP_TILE indices
     __shared__ uint32_t s_warp[CP_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -334,27 +337,22 @@ compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__rest
     if (lane == 31)
         s_warp[warp] = incl;
     __syncthreads();
-    uint32_t before = 0, total = 0;
+    uint32_t before = offsets[tile];
     #pragma unroll
-    for (int w = 0; w < CP_THREADS / 32; ++w) {
-        const uint32_t t = s_warp[w];
-        before += (uint32_t) w < warp ? t : 0;
-        total += t;
+    for (int w = 0; w < CP_THREADS / 32; ++w)
+        before += (uint32_t) w < warp ? s_warp[w] : 0;
+    const uint32_t excl = before + incl - cnt;        // output slot of this word's first set bit
+    const uint32_t item0 = tile * CP_TILE + warp * 1024 - mis + lane; // entry of bit 'lane' of word 0
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t todo = __ballot_sync(FULL_MASK, word != 0);
+    while (todo) {
+        const uint32_t src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t w = __shfl_sync(FULL_MASK, word, src);
+        const uint32_t o = __shfl_sync(FULL_MASK, excl, src);
+        if ((w >> lane) & 1u)
+            out[o + __popc(w & below)] = item0 + src * 32;
     }
-    if (total == 0)
-        return; // CTA-uniform
-    uint32_t o = before + incl - cnt;
-    const uint32_t item0 = tile * CP_TILE + tid * 32 - mis;
-    uint32_t rest = word;
-    while (rest) {
-        const uint32_t b = __ffs(rest) - 1;
-        rest &= rest - 1;
-        cp_stage[o++] = item0 + b;
-    }
-    __syncthreads();
-    uint32_t *dst = out + offsets[tile];
-    for (uint32_t i = tid; i < total; i += CP_THREADS)
-        dst[i] = cp_stage[i];
 }
 
 static int compress_two_pass(cudaStream_t stream, const uint8_t *in, uint64_t size, uint32_t *out,
@@ -377,17 +375,9 @@ static int compress_two_pass(cudaStream_t stream, const uint8_t *in, uint64_t si
             return cuda_fail(err, "cudaMemsetAsync");
         }
     }
-    static std::atomic<bool> attr_set[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev].load(std::memory_order_relaxed)) {
-        cudaFuncSetAttribute(compress_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int) (CP_TILE * 4));
-        attr_set[dev].store(true, std::memory_order_relaxed);
-    }
     compress_pack_kernel<<<(ntiles + 1) / 2, CP_THREADS, 0, stream>>>(in, size, mis, bits, counts, ntiles);
     compress_offsets_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, count_dev);
-    compress_expand_kernel<<<ntiles, CP_THREADS, CP_TILE * 4, stream>>>(bits, counts, mis, out);
+    compress_expand_kernel<<<ntiles, CP_THREADS, 0, stream>>>(bits, counts, mis, out);
     count_launch(2);
     temp_free(bits, stream);
     B200_LAUNCH_CHECK();

@@ -256,6 +256,208 @@ mkperm_offsets_kernel(const uint32_t *__restrict__ starts, uint64_t stride, uint
         records[4 * (size_t) bins] = s_running;
 }
 
+// ------------------------------------------------ single sorting group: tiles
+//
+// block_size == size (what vectorised method dispatch passes): the array is cut
+// into tiles of 8192 keys, one CTA per tile.
+//   tile_hist   per-tile digit counts, written digit-major (table[d][tile]) so
+//               that ONE exclusive scan of the flattened table (scan_fast.cu)
+//               yields the first output slot of every (digit, tile) pair;
+//   tile_place  re-reads the tile, ranks its keys stably (a warp walks its 512
+//               keys in index order, 32 per step: match.any groups equal digits,
+//               the lowest lane advances the warp's private counter), sorts the
+//               tile by digit in shared memory and writes every digit's run with
+//               contiguous stores.  The per-row variant above has every warp
+//               trickle single elements into `bins` output streams at once,
+//               which thrashes L2 (measured on B200: 6.5x DRAM write
+//               amplification, 2-4 ms for 2^26 keys).
+static constexpr int MT_THREADS = 512;
+static constexpr int MT_WARPS = MT_THREADS / 32;
+static constexpr int MT_ITEMS = 16;
+static constexpr uint32_t MT_TILE = MT_THREADS * MT_ITEMS; // 8192 keys
+static constexpr uint32_t MT_MAX_BINS = 1024;              // 10-bit digits
+
+B200_DEVICE uint32_t mt_digit(uint32_t key, uint32_t shift, uint32_t mask, uint32_t bins) {
+    return min((key >> shift) & mask, bins - 1); // out-of-range keys must not corrupt memory
+}
+
+/// table[d * ntiles + tile] = number of keys of the tile whose digit is d.
+/// Dynamic shared memory: copies * bins counters.
+__global__ void __launch_bounds__(MT_THREADS)
+mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32_t ntiles,
+                        uint32_t shift, uint32_t mask, uint32_t bins, uint32_t copies,
+                        uint32_t *__restrict__ table) {
+    extern __shared__ uint32_t mk_smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    for (uint32_t i = tid; i < copies * bins; i += MT_THREADS)
+        mk_smem[i] = 0;
+    __syncthreads();
+    uint32_t *h = mk_smem + (warp % copies) * bins;
+    const uint64_t base = (uint64_t) tile * MT_TILE;
+    if (base + MT_TILE <= size && ((uintptr_t) keys & 15) == 0) {
+        const uint4 *v = (const uint4 *) (keys + base);
+        uint4 k4[MT_ITEMS / 4];
+        #pragma unroll
+        for (int j = 0; j < MT_ITEMS / 4; ++j)
+            k4[j] = ld_stream(v + j * MT_THREADS + tid);
+        #pragma unroll
+        for (int j = 0; j < MT_ITEMS / 4; ++j) {
+            atomicAdd(&h[mt_digit(k4[j].x, shift, mask, bins)], 1u);
+            atomicAdd(&h[mt_digit(k4[j].y, shift, mask, bins)], 1u);
+            atomicAdd(&h[mt_digit(k4[j].z, shift, mask, bins)], 1u);
+            atomicAdd(&h[mt_digit(k4[j].w, shift, mask, bins)], 1u);
+        }
+    } else {
+        #pragma unroll 4
+        for (int j = 0; j < MT_ITEMS; ++j) {
+            const uint64_t g = base + (uint64_t) j * MT_THREADS + tid;
+            if (g < size)
+                atomicAdd(&h[mt_digit(__ldg(keys + g), shift, mask, bins)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t d = tid; d < bins; d += MT_THREADS) {
+        uint32_t c = 0;
+        for (uint32_t r = 0; r < copies; ++r)
+            c += mk_smem[r * bins + d];
+        table[(uint64_t) d * ntiles + tile] = c;
+    }
+}
+
+/// 'table' holds the exclusively scanned counts.  The element moved is
+/// idx_in[g] (PAIRS) or the key's own index g; keys_out (optional) receives the
+/// key at the same slot for the next digit pass.
+/// Dynamic shared memory: 2 * MT_TILE + bins words, then MT_WARPS * (bins + 2)
+/// 16-bit counters.
+template <bool PAIRS>
+__global__ void __launch_bounds__(MT_THREADS, 2)
+mkperm_tile_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ idx_in,
+                         const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
+                         uint32_t shift, uint32_t mask, uint32_t bins,
+                         uint32_t *__restrict__ perm_out, uint32_t *__restrict__ keys_out) {
+    extern __shared__ uint32_t mk_smem[];
+    uint32_t *s_key = mk_smem;
+    uint32_t *s_idx = mk_smem + MT_TILE;
+    uint32_t *s_delta = mk_smem + 2 * MT_TILE;
+    uint16_t *s_hist = (uint16_t *) (mk_smem + 2 * MT_TILE + bins);
+    const uint32_t hstride = bins + 2; // + sentinel bin for the lanes past the end
+    __shared__ uint32_t s_warp[MT_WARPS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t base = (uint64_t) tile * MT_TILE;
+
+    for (uint32_t i = tid; i < MT_WARPS * hstride / 2; i += MT_THREADS)
+        ((uint32_t *) s_hist)[i] = 0;
+
+    // ---- load: warp w owns keys [w * 512, (w + 1) * 512) of the tile, striped
+    uint32_t key[MT_ITEMS];
+    #pragma unroll
+    for (int i = 0; i < MT_ITEMS; ++i) {
+        const uint64_t g = base + warp * 512 + i * 32 + lane;
+        key[i] = g < size ? __ldg(keys + g) : 0u;
+    }
+    __syncthreads();
+
+    // ---- stable rank of every key among the warp's keys with the same digit
+    uint16_t *wh = s_hist + warp * hstride;
+    uint32_t rank2[MT_ITEMS / 2]; // two 16-bit ranks per register (a rank is < 512)
+    #pragma unroll
+    for (int i = 0; i < MT_ITEMS / 2; ++i)
+        rank2[i] = 0;
+    #pragma unroll
+    for (int i = 0; i < MT_ITEMS; ++i) {
+        const uint64_t g = base + warp * 512 + i * 32 + lane;
+        const uint32_t d = g < size ? mt_digit(key[i], shift, mask, bins) : bins;
+        const uint32_t peers = __match_any_sync(FULL_MASK, d);
+        const uint32_t below = __popc(peers & lt_mask);
+        uint32_t old = 0;
+        if (below == 0) {
+            old = wh[d];
+            wh[d] = (uint16_t) (old + __popc(peers));
+        }
+        old = __shfl_sync(FULL_MASK, old, __ffs(peers) - 1);
+        rank2[i / 2] |= (old + below) << (16 * (i & 1));
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over the warps, then over the digits
+    const uint32_t dpt = (bins + MT_THREADS - 1) / MT_THREADS; // digits per thread (<= 2)
+    const uint32_t d0 = tid * dpt;
+    uint32_t cnt[2] = { 0, 0 };
+    #pragma unroll
+    for (uint32_t q = 0; q < 2; ++q) {
+        const uint32_t d = d0 + q;
+        if (q < dpt && d < bins) {
+            uint32_t run = 0;
+            #pragma unroll
+            for (int w = 0; w < MT_WARPS; ++w) {
+                const uint32_t t = s_hist[w * hstride + d];
+                s_hist[w * hstride + d] = (uint16_t) run;
+                run += t;
+            }
+            cnt[q] = run;
+        }
+    }
+    const uint32_t mine = cnt[0] + cnt[1];
+    uint32_t incl = mine;
+    #pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULL_MASK, incl, s);
+        if (lane >= (uint32_t) s)
+            incl += up;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t lstart = incl - mine; // first slot of digit d0 in the sorted tile
+    #pragma unroll
+    for (int w = 0; w < MT_WARPS; ++w)
+        lstart += (uint32_t) w < warp ? s_warp[w] : 0u;
+    #pragma unroll
+    for (uint32_t q = 0; q < 2; ++q) {
+        const uint32_t d = d0 + q;
+        if (q < dpt && d < bins) {
+            // sorted-tile slot j of this digit goes to global slot j + delta
+            s_delta[d] = __ldg(table + (uint64_t) d * ntiles + tile) - lstart;
+            #pragma unroll
+            for (int w = 0; w < MT_WARPS; ++w)
+                s_hist[w * hstride + d] = (uint16_t) (s_hist[w * hstride + d] + lstart);
+            lstart += cnt[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- sort the tile by digit in shared memory
+    #pragma unroll
+    for (int i = 0; i < MT_ITEMS; ++i) {
+        const uint64_t g = base + warp * 512 + i * 32 + lane;
+        if (g < size) {
+            const uint32_t d = mt_digit(key[i], shift, mask, bins);
+            const uint32_t slot = wh[d] + ((rank2[i / 2] >> (16 * (i & 1))) & 0xffffu);
+            s_key[slot] = key[i];
+            s_idx[slot] = PAIRS ? __ldg(idx_in + g) : (uint32_t) g;
+        }
+    }
+    __syncthreads();
+
+    // ---- write every digit's run with contiguous stores
+    const uint32_t tile_count = (uint32_t) min((uint64_t) MT_TILE, size - base);
+    for (uint32_t j = tid; j < tile_count; j += MT_THREADS) {
+        const uint32_t k = s_key[j];
+        const uint32_t pos = j + s_delta[mt_digit(k, shift, mask, bins)];
+        perm_out[pos] = s_idx[j];
+        if (keys_out)
+            keys_out[pos] = k;
+    }
+}
+
+static size_t tile_place_smem(uint32_t bins) {
+    return (size_t) (2 * MT_TILE + bins) * 4 + (size_t) MT_WARPS * (bins + 2) * 2;
+}
+
 static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t size,
                             uint32_t bins, uint32_t *hist) {
     B200_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t) bins * sizeof(uint32_t), stream));
@@ -326,11 +528,14 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     uint32_t total_bits = 0;
     while (total_bits < 32 && (1ull << total_bits) < bucket_count)
         total_bits++;
+    const bool tiled = ngroups == 1; // one sorting group: tile kernels
+    const uint32_t digit_bits = tiled ? 10 : 11;
     uint32_t npasses = 1, bits_per = 0;
-    if (bucket_count > MKPERM_MAX_BINS) {
-        npasses = (total_bits + 10) / 11;
+    if (bucket_count > (tiled ? MT_MAX_BINS : MKPERM_MAX_BINS)) {
+        npasses = (total_bits + digit_bits - 1) / digit_bits;
         bits_per = (total_bits + npasses - 1) / npasses;
     }
+    const uint32_t ntiles = (uint32_t) ceil_div(size, MT_TILE);
 
     // ---- row geometry (shared by all passes)
     uint32_t max_bins = npasses == 1 ? bucket_count : (1u << bits_per);
@@ -343,7 +548,14 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     }
 
     size_t smem = (size_t) MKPERM_WARPS * max_bins * sizeof(uint32_t);
-    if (smem > 48 * 1024) {
+    if (tiled) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_place_kernel<false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int) tile_place_smem(MT_MAX_BINS)));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_place_kernel<true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int) tile_place_smem(MT_MAX_BINS)));
+    } else if (smem > 48 * 1024) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_hist_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_place_kernel,
@@ -351,7 +563,7 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     }
 
     // groups per launch so that the count table stays below 1 GiB
-    uint64_t counts_per_group = (uint64_t) max_bins * rows_per_group;
+    uint64_t counts_per_group = (uint64_t) max_bins * (tiled ? ntiles : rows_per_group);
     uint64_t groups_per_launch = std::max<uint64_t>(1, (1ull << 28) / counts_per_group);
     groups_per_launch = std::min(groups_per_launch, ngroups);
     if (counts_per_group >= (1ull << 31))
@@ -398,6 +610,46 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
         uint32_t *keys_out = last ? nullptr : tmp[(pass & 1) * 2];
         uint32_t *idx_out = last ? perm : tmp[(pass & 1) * 2 + 1];
         size_t pass_smem = (size_t) MKPERM_WARPS * g.bins * sizeof(uint32_t);
+
+        if (tiled) {
+            const uint64_t ncounts = (uint64_t) g.bins * ntiles;
+            // replicate small histograms over the warps of a CTA (less contention)
+            uint32_t copies = std::max<uint32_t>(1, std::min<uint32_t>(MT_WARPS, 4096 / g.bins));
+            mkperm_tile_hist_kernel<<<ntiles, MT_THREADS, (size_t) copies * g.bins * 4, stream>>>(
+                keys_in, size, ntiles, g.shift, g.mask, g.bins, copies, counts);
+            count_launch();
+            rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts, ncounts, 1, 0,
+                                          counts, counts);
+            if (rc) {
+                cleanup();
+                return rc;
+            }
+            // single pass: bucket starts are a strided view of the scanned table
+            if (last && npasses == 1 && offsets) {
+                uint32_t *records = (uint32_t *) temp_alloc(((size_t) bucket_count * 4 + 1) * 4, stream);
+                if (!records) {
+                    cleanup();
+                    return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
+                }
+                mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, bucket_count, size, records);
+                count_launch();
+                cudaError_t err = cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
+                                                  cudaMemcpyDeviceToHost, stream);
+                temp_free(records, stream);
+                if (err != cudaSuccess) {
+                    cleanup();
+                    return cuda_fail(err, "cudaMemcpyAsync(offsets)");
+                }
+            }
+            if (idx_in)
+                mkperm_tile_place_kernel<true><<<ntiles, MT_THREADS, tile_place_smem(g.bins), stream>>>(
+                    keys_in, idx_in, counts, size, ntiles, g.shift, g.mask, g.bins, idx_out, keys_out);
+            else
+                mkperm_tile_place_kernel<false><<<ntiles, MT_THREADS, tile_place_smem(g.bins), stream>>>(
+                    keys_in, idx_in, counts, size, ntiles, g.shift, g.mask, g.bins, idx_out, keys_out);
+            count_launch();
+            continue;
+        }
 
         for (uint64_t g0 = 0; g0 < ngroups; g0 += groups_per_launch) {
             g.group0 = g0;
