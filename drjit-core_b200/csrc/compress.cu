@@ -262,23 +262,28 @@ compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis
     }
 }
 
-/// In-place exclusive scan of the tile counts by one CTA; total -> *count_out.
+/// In-place exclusive scan of the tile counts by one CTA (16 counts per thread
+/// and step, loaded up front); total -> *count_out.
 __global__ void __launch_bounds__(1024)
 compress_offsets_kernel(uint32_t *__restrict__ counts, uint32_t ntiles,
                         uint32_t *__restrict__ count_out) {
+    constexpr int PER = 16;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0)
         s_carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < ntiles; base += 4096) {
-        const uint32_t i = base + tid * 4;
-        uint32_t c[4];
+    for (uint32_t base = 0; base < ntiles; base += 1024 * PER) {
+        const uint32_t i = base + tid * PER;
+        uint32_t c[PER];
         #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < PER; ++k)
             c[k] = i + k < ntiles ? counts[i + k] : 0;
-        const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+        uint32_t mine = 0;
+        #pragma unroll
+        for (int k = 0; k < PER; ++k)
+            mine += c[k];
         uint32_t incl = mine;
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -299,7 +304,7 @@ compress_offsets_kernel(uint32_t *__restrict__ counts, uint32_t ntiles,
         const uint32_t carry = s_carry;
         uint32_t run = carry + __shfl_sync(FULL_MASK, wincl - wsum, warp) + incl - mine;
         #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < PER; ++k) {
             if (i + k < ntiles)
                 counts[i + k] = run;
             run += c[k];
@@ -313,45 +318,64 @@ compress_offsets_kernel(uint32_t *__restrict__ counts, uint32_t ntiles,
         *count_out = s_carry;
 }
 
-/// One tile of 8192 entries per CTA, one bit-mask word per thread.  After the
-/// block-wide exclusive scan of the popcounts a warp walks its non-empty words:
-/// the word and its output offset are broadcast, lane j owns bit j and stores the
-/// index at offset + (number of set bits below j).  Set bits of a word land on
-/// consecutive addresses, so every store instruction writes one contiguous run
-/// (no shared-memory staging, no bank conflicts).
+/// CP_EXP consecutive tiles of 8192 entries per CTA, one bit-mask word per thread
+/// and tile (all loaded up front).  After the block-wide exclusive scan of the
+/// popcounts a warp walks its non-empty words: the word and its output offset
+/// are broadcast, lane j owns bit j and stores the index at offset + (number of
+/// set bits below j).  Set bits of a word land on consecutive addresses, so every
+/// store instruction writes one contiguous run (no shared-memory staging).
+static constexpr uint32_t CP_EXP = 4;
+
 __global__ void __launch_bounds__(CP_THREADS)
 compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ offsets,
-                       uint32_t mis, uint32_t *__restrict__ out) {
-    __shared__ uint32_t s_warp[CP_THREADS / 32];
+                       uint32_t ntiles, uint32_t mis, uint32_t *__restrict__ out) {
+    __shared__ uint32_t s_warp[CP_EXP][CP_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t word = __ldg(bits + (uint64_t) tile * CP_WORDS + tid);
-    const uint32_t cnt = __popc(word);
-    uint32_t incl = cnt;
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
-        if (lane >= (uint32_t) d)
-            incl += up;
-    }
-    if (lane == 31)
-        s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t before = offsets[tile];
-    #pragma unroll
-    for (int w = 0; w < CP_THREADS / 32; ++w)
-        before += (uint32_t) w < warp ? s_warp[w] : 0;
-    const uint32_t excl = before + incl - cnt;        // output slot of this word's first set bit
-    const uint32_t item0 = tile * CP_TILE + warp * 1024 - mis + lane; // entry of bit 'lane' of word 0
+    const uint32_t tile0 = blockIdx.x * CP_EXP;
     const uint32_t below = (1u << lane) - 1u;
-    uint32_t todo = __ballot_sync(FULL_MASK, word != 0);
-    while (todo) {
-        const uint32_t src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t w = __shfl_sync(FULL_MASK, word, src);
-        const uint32_t o = __shfl_sync(FULL_MASK, excl, src);
-        if ((w >> lane) & 1u)
-            out[o + __popc(w & below)] = item0 + src * 32;
+
+    uint32_t word[CP_EXP], excl[CP_EXP];
+    #pragma unroll
+    for (uint32_t t = 0; t < CP_EXP; ++t)
+        word[t] = tile0 + t < ntiles ? __ldg(bits + (uint64_t) (tile0 + t) * CP_WORDS + tid) : 0u;
+    #pragma unroll
+    for (uint32_t t = 0; t < CP_EXP; ++t) {
+        const uint32_t cnt = __popc(word[t]);
+        uint32_t incl = cnt;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= (uint32_t) d)
+                incl += up;
+        }
+        if (lane == 31)
+            s_warp[t][warp] = incl;
+        excl[t] = incl - cnt;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (uint32_t t = 0; t < CP_EXP; ++t) {
+        if (tile0 + t >= ntiles)
+            break;
+        uint32_t before = __ldg(offsets + tile0 + t);
+        #pragma unroll
+        for (int w = 0; w < CP_THREADS / 32; ++w)
+            before += (uint32_t) w < warp ? s_warp[t][w] : 0u;
+        const uint32_t first = before + excl[t]; // output slot of this word's first set bit
+        const uint32_t item0 = (tile0 + t) * CP_TILE + warp * 1024 - mis + lane; // bit 'lane' of word 0
+        const uint32_t nz = __ballot_sync(FULL_MASK, word[t] != 0);
+        #pragma unroll 1
+        for (uint32_t g = 0; g < 32; g += 4) {
+            if (((nz >> g) & 0xfu) == 0)
+                continue; // warp-uniform
+            #pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t w = __shfl_sync(FULL_MASK, word[t], g + u);
+                const uint32_t o = __shfl_sync(FULL_MASK, first, g + u);
+                if ((w >> lane) & 1u)
+                    out[o + __popc(w & below)] = item0 + (g + u) * 32;
+            }
+        }
     }
 }
 
@@ -377,7 +401,7 @@ static int compress_two_pass(cudaStream_t stream, const uint8_t *in, uint64_t si
     }
     compress_pack_kernel<<<(ntiles + 1) / 2, CP_THREADS, 0, stream>>>(in, size, mis, bits, counts, ntiles);
     compress_offsets_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, count_dev);
-    compress_expand_kernel<<<ntiles, CP_THREADS, 0, stream>>>(bits, counts, mis, out);
+    compress_expand_kernel<<<(uint32_t) ceil_div(ntiles, CP_EXP), CP_THREADS, 0, stream>>>(bits, counts, ntiles, mis, out);
     count_launch(2);
     temp_free(bits, stream);
     B200_LAUNCH_CHECK();

@@ -281,47 +281,67 @@ B200_DEVICE uint32_t mt_digit(uint32_t key, uint32_t shift, uint32_t mask, uint3
     return min((key >> shift) & mask, bins - 1); // out-of-range keys must not corrupt memory
 }
 
-/// table[d * ntiles + tile] = number of keys of the tile whose digit is d.
-/// Dynamic shared memory: copies * bins counters.
+/// table[d * ntiles + tile] = number of keys of the tile whose digit is d.  A CTA
+/// counts MT_GROUP consecutive tiles into one shared-memory histogram each, so
+/// that the MT_GROUP entries of a digit are contiguous in the digit-major table
+/// (one 32-byte run instead of MT_GROUP scattered words).
+/// Dynamic shared memory: MT_GROUP * bins counters.
+static constexpr uint32_t MT_GROUP = 8;
+
 __global__ void __launch_bounds__(MT_THREADS)
 mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32_t ntiles,
-                        uint32_t shift, uint32_t mask, uint32_t bins, uint32_t copies,
+                        uint32_t shift, uint32_t mask, uint32_t bins,
                         uint32_t *__restrict__ table) {
     extern __shared__ uint32_t mk_smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
-    for (uint32_t i = tid; i < copies * bins; i += MT_THREADS)
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile0 = blockIdx.x * MT_GROUP;
+    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS)
         mk_smem[i] = 0;
     __syncthreads();
-    uint32_t *h = mk_smem + (warp % copies) * bins;
-    const uint64_t base = (uint64_t) tile * MT_TILE;
-    if (base + MT_TILE <= size && ((uintptr_t) keys & 15) == 0) {
-        const uint4 *v = (const uint4 *) (keys + base);
-        uint4 k4[MT_ITEMS / 4];
+    const bool aligned = ((uintptr_t) keys & 15) == 0;
+    #pragma unroll 1
+    for (uint32_t t = 0; t < MT_GROUP; t += 2) {
+        // two tiles per step: 8 x 16-byte loads in flight per thread
+        uint4 k4[2][MT_ITEMS / 4];
+        bool full[2];
         #pragma unroll
-        for (int j = 0; j < MT_ITEMS / 4; ++j)
-            k4[j] = ld_stream(v + j * MT_THREADS + tid);
-        #pragma unroll
-        for (int j = 0; j < MT_ITEMS / 4; ++j) {
-            atomicAdd(&h[mt_digit(k4[j].x, shift, mask, bins)], 1u);
-            atomicAdd(&h[mt_digit(k4[j].y, shift, mask, bins)], 1u);
-            atomicAdd(&h[mt_digit(k4[j].z, shift, mask, bins)], 1u);
-            atomicAdd(&h[mt_digit(k4[j].w, shift, mask, bins)], 1u);
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t base = (uint64_t) (tile0 + t + u) * MT_TILE;
+            full[u] = aligned && base + MT_TILE <= size;
+            if (full[u]) {
+                const uint4 *v = (const uint4 *) (keys + base);
+                #pragma unroll
+                for (int j = 0; j < MT_ITEMS / 4; ++j)
+                    k4[u][j] = ld_stream(v + j * MT_THREADS + tid);
+            }
         }
-    } else {
-        #pragma unroll 4
-        for (int j = 0; j < MT_ITEMS; ++j) {
-            const uint64_t g = base + (uint64_t) j * MT_THREADS + tid;
-            if (g < size)
-                atomicAdd(&h[mt_digit(__ldg(keys + g), shift, mask, bins)], 1u);
+        #pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uint32_t *h = mk_smem + (t + u) * bins;
+            const uint64_t base = (uint64_t) (tile0 + t + u) * MT_TILE;
+            if (full[u]) {
+                #pragma unroll
+                for (int j = 0; j < MT_ITEMS / 4; ++j) {
+                    atomicAdd(&h[mt_digit(k4[u][j].x, shift, mask, bins)], 1u);
+                    atomicAdd(&h[mt_digit(k4[u][j].y, shift, mask, bins)], 1u);
+                    atomicAdd(&h[mt_digit(k4[u][j].z, shift, mask, bins)], 1u);
+                    atomicAdd(&h[mt_digit(k4[u][j].w, shift, mask, bins)], 1u);
+                }
+            } else if (base < size) {
+                #pragma unroll 4
+                for (int j = 0; j < MT_ITEMS; ++j) {
+                    const uint64_t g = base + (uint64_t) j * MT_THREADS + tid;
+                    if (g < size)
+                        atomicAdd(&h[mt_digit(__ldg(keys + g), shift, mask, bins)], 1u);
+                }
+            }
         }
     }
     __syncthreads();
-    for (uint32_t d = tid; d < bins; d += MT_THREADS) {
-        uint32_t c = 0;
-        for (uint32_t r = 0; r < copies; ++r)
-            c += mk_smem[r * bins + d];
-        table[(uint64_t) d * ntiles + tile] = c;
+    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS) {
+        const uint32_t d = i / MT_GROUP, t = i % MT_GROUP;
+        if (tile0 + t < ntiles)
+            table[(uint64_t) d * ntiles + tile0 + t] = mk_smem[t * bins + d];
     }
 }
 
@@ -341,7 +361,8 @@ mkperm_tile_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__re
     uint32_t *s_idx = mk_smem + MT_TILE;
     uint32_t *s_delta = mk_smem + 2 * MT_TILE;
     uint16_t *s_hist = (uint16_t *) (mk_smem + 2 * MT_TILE + bins);
-    const uint32_t hstride = bins + 2; // + sentinel bin for the lanes past the end
+    // 16-bit counters, two per word; + sentinel bin for the lanes past the end
+    const uint32_t hstride = (bins + 3) & ~1u;
     __shared__ uint32_t s_warp[MT_WARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -359,49 +380,60 @@ mkperm_tile_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__re
         const uint64_t g = base + warp * 512 + i * 32 + lane;
         key[i] = g < size ? __ldg(keys + g) : 0u;
     }
+    // first output slot of this thread's digits in this tile (used much later)
+    const uint32_t dpt = (bins + MT_THREADS - 1) / MT_THREADS; // digits per thread (<= 2)
+    const uint32_t d0 = tid * dpt;
+    uint32_t gstart[2] = { 0, 0 };
+    #pragma unroll
+    for (uint32_t q = 0; q < 2; ++q)
+        if (q < dpt && d0 + q < bins)
+            gstart[q] = __ldg(table + (uint64_t) (d0 + q) * ntiles + tile);
     __syncthreads();
 
-    // ---- stable rank of every key among the warp's keys with the same digit
-    uint16_t *wh = s_hist + warp * hstride;
+    // ---- stable rank of every key among the warp's keys with the same digit:
+    // match.any groups the lanes with equal digits, the lowest lane of a group
+    // advances the warp's private counter, everyone takes counter + (number of
+    // group members below it).  (A variant that batches the 16 match / atomic /
+    // shuffle steps to break the dependency chain measured 20 % slower: more
+    // live registers than the 64 that two CTAs per SM allow.)
     uint32_t rank2[MT_ITEMS / 2]; // two 16-bit ranks per register (a rank is < 512)
     #pragma unroll
     for (int i = 0; i < MT_ITEMS / 2; ++i)
         rank2[i] = 0;
-    #pragma unroll
-    for (int i = 0; i < MT_ITEMS; ++i) {
-        const uint64_t g = base + warp * 512 + i * 32 + lane;
-        const uint32_t d = g < size ? mt_digit(key[i], shift, mask, bins) : bins;
-        const uint32_t peers = __match_any_sync(FULL_MASK, d);
-        const uint32_t below = __popc(peers & lt_mask);
-        uint32_t old = 0;
-        if (below == 0) {
-            old = wh[d];
-            wh[d] = (uint16_t) (old + __popc(peers));
+    {
+        uint16_t *whr = s_hist + warp * hstride;
+        #pragma unroll
+        for (int i = 0; i < MT_ITEMS; ++i) {
+            const uint64_t g = base + warp * 512 + i * 32 + lane;
+            const uint32_t d = g < size ? mt_digit(key[i], shift, mask, bins) : bins;
+            const uint32_t peers = __match_any_sync(FULL_MASK, d);
+            const uint32_t below = __popc(peers & lt_mask);
+            uint32_t old = 0;
+            if (below == 0) {
+                old = whr[d];
+                whr[d] = (uint16_t) (old + __popc(peers));
+            }
+            old = __shfl_sync(FULL_MASK, old, __ffs(peers) - 1);
+            rank2[i / 2] |= (old + below) << (16 * (i & 1));
         }
-        old = __shfl_sync(FULL_MASK, old, __ffs(peers) - 1);
-        rank2[i / 2] |= (old + below) << (16 * (i & 1));
     }
+    uint16_t *wh = s_hist + warp * hstride;
     __syncthreads();
 
-    // ---- per digit: exclusive prefix over the warps, then over the digits
-    const uint32_t dpt = (bins + MT_THREADS - 1) / MT_THREADS; // digits per thread (<= 2)
-    const uint32_t d0 = tid * dpt;
-    uint32_t cnt[2] = { 0, 0 };
-    #pragma unroll
-    for (uint32_t q = 0; q < 2; ++q) {
-        const uint32_t d = d0 + q;
-        if (q < dpt && d < bins) {
-            uint32_t run = 0;
-            #pragma unroll
-            for (int w = 0; w < MT_WARPS; ++w) {
-                const uint32_t t = s_hist[w * hstride + d];
-                s_hist[w * hstride + d] = (uint16_t) run;
-                run += t;
-            }
-            cnt[q] = run;
-        }
+    // ---- per digit: total over the warps, exclusive prefix over the digits,
+    // then every warp's first slot of the digit in the sorted tile
+    uint32_t cnt0 = 0, cnt1 = 0;
+    if (d0 < bins) {
+        #pragma unroll
+        for (int w = 0; w < MT_WARPS; ++w)
+            cnt0 += s_hist[w * hstride + d0];
     }
-    const uint32_t mine = cnt[0] + cnt[1];
+    if (dpt > 1 && d0 + 1 < bins) {
+        #pragma unroll
+        for (int w = 0; w < MT_WARPS; ++w)
+            cnt1 += s_hist[w * hstride + d0 + 1];
+    }
+    const uint32_t mine = cnt0 + cnt1;
     uint32_t incl = mine;
     #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
@@ -421,11 +453,15 @@ mkperm_tile_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__re
         const uint32_t d = d0 + q;
         if (q < dpt && d < bins) {
             // sorted-tile slot j of this digit goes to global slot j + delta
-            s_delta[d] = __ldg(table + (uint64_t) d * ntiles + tile) - lstart;
-            #pragma unroll
-            for (int w = 0; w < MT_WARPS; ++w)
-                s_hist[w * hstride + d] = (uint16_t) (s_hist[w * hstride + d] + lstart);
-            lstart += cnt[q];
+            s_delta[d] = gstart[q] - lstart;
+            uint32_t run = lstart;
+            #pragma unroll 4
+            for (int w = 0; w < MT_WARPS; ++w) {
+                const uint32_t t = s_hist[w * hstride + d];
+                s_hist[w * hstride + d] = (uint16_t) run;
+                run += t;
+            }
+            lstart = run;
         }
     }
     __syncthreads();
@@ -455,7 +491,7 @@ mkperm_tile_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__re
 }
 
 static size_t tile_place_smem(uint32_t bins) {
-    return (size_t) (2 * MT_TILE + bins) * 4 + (size_t) MT_WARPS * (bins + 2) * 2;
+    return (size_t) (2 * MT_TILE + bins) * 4 + (size_t) MT_WARPS * ((bins + 3) & ~1u) * 2;
 }
 
 static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t size,
@@ -613,10 +649,9 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
 
         if (tiled) {
             const uint64_t ncounts = (uint64_t) g.bins * ntiles;
-            // replicate small histograms over the warps of a CTA (less contention)
-            uint32_t copies = std::max<uint32_t>(1, std::min<uint32_t>(MT_WARPS, 4096 / g.bins));
-            mkperm_tile_hist_kernel<<<ntiles, MT_THREADS, (size_t) copies * g.bins * 4, stream>>>(
-                keys_in, size, ntiles, g.shift, g.mask, g.bins, copies, counts);
+            mkperm_tile_hist_kernel<<<(uint32_t) ceil_div(ntiles, MT_GROUP), MT_THREADS,
+                                      (size_t) MT_GROUP * g.bins * 4, stream>>>(
+                keys_in, size, ntiles, g.shift, g.mask, g.bins, counts);
             count_launch();
             rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts, ncounts, 1, 0,
                                           counts, counts);
