@@ -23,7 +23,7 @@ whole-array reduce / scan (bs = global size) go through the sharded front end
 rank + local single-pass scan seeded with the rank's carry).
 
 Printed keys (one JSON line, rank 0): the contract of the build driver plus
-  roofline      dominant kernel (scan_kernel<float, Add>): algorithmic bytes
+  roofline      dominant kernel (scan_stream_kernel<float, Add>): algorithmic bytes
                 per launch / mean launch duration from CUDA events recorded
                 inside the timed region, against MEASURED_PEAKS.json
   e2e           same step through the C-ABI with HOST (pinned) input and output
@@ -415,7 +415,7 @@ def run_b200_arm(args):
     ms_per_step = total_ms_max / K
     value = world * len(calls) * n / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel: scan_kernel<float, Add> (bs > 1)
+    # ---- roofline of the dominant kernel: scan_stream_kernel<float, Add> (1 < bs <= 4096)
     peak, peak_kind = load_peaks()
     mean_call = per_call.mean(axis=0)
     scan_idx = [c for c, (kind, bs) in enumerate(calls) if kind == "scan" and bs > 1 and bs < n_global]
@@ -424,7 +424,7 @@ def run_b200_arm(args):
     achieved = 8.0 * n / (scan_ms * 1e-3) / 1e9
     traffic = load_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "scan_kernel<float, Add, J=4> (jit_block_prefix_reduce, bs 2..4096)",
+        "bound": "hbm", "kernel": "scan_stream_kernel<float, Add, 4, 3, 512, CHAIN=false> (jit_block_prefix_reduce, bs 2..4096)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
         "frac_of_nominal_8000": achieved / 8000.0,
