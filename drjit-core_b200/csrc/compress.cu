@@ -14,6 +14,7 @@
 //     per mask byte (compress.cuh:146-149).
 // Larger masks take the bit-packed two-pass path further down.
 #include "common.cuh"
+#include "pipeline.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -379,6 +380,335 @@ compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__rest
     }
 }
 
+// ------------------------------------------------------- single-pass stream
+//
+// Large masks, one launch: the mask is read exactly once (1 byte per entry), the
+// indices are written exactly once -- the algorithmic n + 4 count bytes.
+//
+// What makes a single pass cheap here is that a packed tile is tiny: a thread
+// reduces its J 16-byte vectors (J * 16 entries) to J 16-bit words kept in J / 2
+// registers, so a CTA can hold TWO tiles at once and run a software pipeline
+// around the one unavoidable latency, the look-back:
+//
+//   iteration k   compute warps: mask of tile k arrives in registers (loads were
+//                 issued an iteration ago) -> pack to bits -> issue the loads of
+//                 tile k + 1 -> publish the warp totals -> barrier -> EXPAND
+//                 TILE k - 1, whose prefix was resolved in the meantime;
+//                 look-back warp: after the same barrier publishes the aggregate
+//                 of tile k, resolves its exclusive prefix over 64-bit
+//                 {status, count} descriptors and leaves it for iteration k + 1.
+//
+// Persistent CTAs (two per SM), tiles handed out by an atomic ticket two
+// iterations ahead (forward progress of the look-back + load balance).
+//
+// Layout of a tile (virtual bytes, i.e. relative to the 16-byte aligned address
+// in - mis): warp w owns the contiguous bytes [w * J * 512, (w + 1) * J * 512),
+// vector j of lane l covers bytes j * 512 + l * 16 ... + 16 of that range, so a
+// load instruction of a warp reads 512 contiguous bytes.
+//
+// Expansion of a row (512 entries = one 16-bit word per lane):
+//   dense   (> CS_SPARSE set entries): the row is walked two lanes' words at a
+//           time; the words and their output offsets are broadcast, lane i owns
+//           bit i & 15 of word i >> 4 and stores its index at offset + (number of
+//           set bits below it): every store instruction writes one or two
+//           contiguous runs.
+//   sparse  every lane walks the set bits of its own word (a few iterations).
+
+static constexpr int CS_THREADS = 512;             // compute threads (+ 32: look-back warp)
+static constexpr int CS_WARPS = CS_THREADS / 32;
+static constexpr uint32_t CS_SPARSE = 48;          // set entries per 512-entry row
+static constexpr uint32_t CS_NONE = 0xffffffffu;
+
+template <int J>
+__global__ void __launch_bounds__(CS_THREADS + 32, 2)
+compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t size,
+                       uint32_t mis, uint32_t ntiles, uint64_t *desc, uint32_t *ticket,
+                       uint32_t *count_out) {
+    static_assert(J % 2 == 0 && J <= 8, "J 16-bit words are kept in J / 2 registers");
+    constexpr uint32_t WARP_BYTES = J * 512;
+    constexpr uint32_t TILE = CS_WARPS * WARP_BYTES;
+
+    __shared__ uint32_t s_tile[4];            // tile of iteration k in s_tile[k % 4]
+    __shared__ uint32_t s_wtot[2][CS_WARPS];  // set entries per warp of tile k in [k & 1]
+    __shared__ uint32_t s_prefix[2];          // exclusive prefix of tile k in [k & 1]
+    __shared__ __align__(8) uint64_t s_full[CS_WARPS]; // the warp's part of a tile has landed
+    extern __shared__ __align__(128) uint8_t cs_smem[]; // CS_WARPS * WARP_BYTES
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *vin = in - mis;
+    const uint64_t vend = size + mis; // valid virtual bytes: [mis, vend)
+
+    if (tid == 0) {
+        #pragma unroll
+        for (int w = 0; w < CS_WARPS; ++w)
+            mbar_init(&s_full[w], 1);
+        mbar_fence_init();
+        const uint32_t t0 = atomicAdd(ticket, 1u), t1 = atomicAdd(ticket, 1u);
+        s_tile[0] = t0 < ntiles ? t0 : CS_NONE;
+        s_tile[1] = t1 < ntiles ? t1 : CS_NONE;
+    }
+    __syncthreads();
+
+    // ---- look-back warp
+    if (warp == CS_WARPS) {
+        for (uint32_t k = 0;; ++k) {
+            __syncthreads(); // warp totals of tile k are in s_wtot[k & 1]
+            const uint32_t tile = s_tile[k % 4];
+            if (tile == CS_NONE)
+                break;
+            const uint32_t total = __reduce_add_sync(FULL_MASK, lane < CS_WARPS ? s_wtot[k & 1][lane] : 0u);
+            uint32_t prefix = 0;
+            if (tile == 0) {
+                if (lane == 0)
+                    Desc<uint32_t>::publish(desc, 0, DESC_PREFIX, total);
+            } else {
+                if (lane == 0)
+                    Desc<uint32_t>::publish(desc, tile, DESC_AGGREGATE, total);
+                int64_t win = (int64_t) tile - 1;
+                while (true) {
+                    // window of the 32 preceding tiles, lane 0 nearest; only lanes
+                    // whose entry is still INVALID poll again, entries beyond the
+                    // nearest PREFIX are not waited for
+                    const int64_t idx = win - lane;
+                    uint32_t val = 0, st = DESC_PREFIX, pre;
+                    if (idx >= 0)
+                        st = Desc<uint32_t>::observe(desc, (uint32_t) idx, val);
+                    while (true) {
+                        pre = __ballot_sync(FULL_MASK, st == DESC_PREFIX);
+                        uint32_t inv = __ballot_sync(FULL_MASK, st == DESC_INVALID);
+                        if (pre)
+                            inv &= (1u << (__ffs(pre) - 1)) - 1u;
+                        if (!inv)
+                            break;
+                        __nanosleep(64);
+                        if (st == DESC_INVALID)
+                            st = Desc<uint32_t>::observe(desc, (uint32_t) idx, val);
+                    }
+                    if (pre) {
+                        const uint32_t stop = __ffs(pre) - 1;
+                        prefix += __reduce_add_sync(FULL_MASK, lane <= stop ? val : 0u);
+                        break;
+                    }
+                    prefix += __reduce_add_sync(FULL_MASK, val);
+                    win -= 32;
+                }
+                if (lane == 0)
+                    Desc<uint32_t>::publish(desc, tile, DESC_PREFIX, prefix + total);
+            }
+            if (lane == 0) {
+                s_prefix[k & 1] = prefix;
+                if (tile == ntiles - 1)
+                    *count_out = prefix + total;
+            }
+        }
+        return;
+    }
+
+    // ---- compute warps
+    // The mask of a tile reaches shared memory through one 1-D bulk copy per warp
+    // (the warp's J * 512 bytes are contiguous), issued by lane 0 an iteration
+    // ahead and tracked by the warp's own mbarrier.  Tiles that are not entirely
+    // inside the array (a misaligned head, the tail) are read with guarded loads.
+    uint4 *wbuf = (uint4 *) cs_smem + (size_t) warp * (WARP_BYTES / 16);
+    auto tile_is_full = [&](uint32_t tile) {
+        return (uint64_t) tile * TILE >= mis && (uint64_t) (tile + 1) * TILE <= vend;
+    };
+    auto request_tile = [&](uint32_t tile) { // lane 0 only
+        if (tile_is_full(tile)) {
+            mbar_arrive_expect_tx(&s_full[warp], WARP_BYTES);
+            bulk_g2s(wbuf, vin + (uint64_t) tile * TILE + warp * WARP_BYTES, WARP_BYTES, &s_full[warp]);
+        } else {
+            mbar_arrive(&s_full[warp]);
+        }
+    };
+    auto fetch_vector = [&](uint32_t tile, bool full, int j) -> uint4 {
+        if (full)
+            return wbuf[j * 32 + lane];
+        const uint64_t vb = (uint64_t) tile * TILE + warp * WARP_BYTES + j * 512 + lane * 16;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (vb >= mis && vb + 16 <= vend) {
+            x = ld_stream(vin + vb);
+        } else if (vb < vend && vb + 16 > mis) {
+            uint32_t w[4] = { 0, 0, 0, 0 };
+            #pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if (vb + b >= mis && vb + b < vend)
+                    w[b >> 2] |= (uint32_t) vin[vb + b] << (8 * (b & 3));
+            x = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return x;
+    };
+
+    // expansion of one tile held as packed bits (hp[q] = word of row 2q | word of
+    // row 2q + 1 << 16); 'first' = output slot of the warp's first set entry
+    auto expand = [&](uint32_t tile, const uint32_t (&hp)[J / 2], uint32_t first) {
+        // inclusive scans over the lanes of all J row counts at once: three
+        // 10-bit fields per register (a row holds at most 512 set entries)
+        constexpr int NP = (J + 2) / 3;
+        uint32_t c[J], P[NP];
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            c[j] = __popc((hp[j / 2] >> (16 * (j & 1))) & 0xffffu);
+        #pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            P[i] = 0;
+            #pragma unroll
+            for (int f = 0; f < 3; ++f)
+                if (i * 3 + f < J)
+                    P[i] |= c[i * 3 + f] << (10 * f);
+        }
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            #pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const uint32_t up = __shfl_up_sync(FULL_MASK, P[i], d);
+                if (lane >= (uint32_t) d)
+                    P[i] += up;
+            }
+        }
+        uint32_t T[NP];
+        #pragma unroll
+        for (int i = 0; i < NP; ++i)
+            T[i] = __shfl_sync(FULL_MASK, P[i], 31);
+
+        // entry index of bit 0 of this lane's word of row 0 (may wrap below zero
+        // for the masked-out head bytes, which are never set)
+        const uint32_t item0 = (uint32_t) ((uint64_t) tile * TILE + warp * WARP_BYTES + lane * 16 - mis);
+        const uint32_t sub = lane & 15, below = (1u << sub) - 1u;
+        uint32_t row_first = first;
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const uint32_t row_total = (T[j / 3] >> (10 * (j % 3))) & 0x3ffu;
+            if (row_total == 0)
+                continue; // warp-uniform
+            const uint32_t incl = (P[j / 3] >> (10 * (j % 3))) & 0x3ffu;
+            uint32_t word = (hp[j / 2] >> (16 * (j & 1))) & 0xffffu;
+            uint32_t o = row_first + incl - c[j]; // slot of this lane's first set entry
+            if (row_total <= CS_SPARSE) {
+                uint32_t item = item0 + j * 512;
+                while (word) {
+                    const uint32_t b = __ffs(word) - 1;
+                    word &= word - 1;
+                    out[o++] = item + b;
+                }
+            } else {
+                const uint32_t nz = __ballot_sync(FULL_MASK, word != 0);
+                // item of bit 'sub' of the word of lane (lane >> 4)
+                const uint32_t item = item0 - lane * 16 + j * 512 + (lane >> 4) * 16 + sub;
+                #pragma unroll 4
+                for (uint32_t s = 0; s < 16; ++s) {
+                    if (((nz >> (2 * s)) & 3u) == 0)
+                        continue; // warp-uniform
+                    const uint32_t src = 2 * s + (lane >> 4);
+                    const uint32_t w = __shfl_sync(FULL_MASK, word, src);
+                    const uint32_t wo = __shfl_sync(FULL_MASK, o, src);
+                    if ((w >> sub) & 1u)
+                        out[wo + __popc(w & below)] = item + s * 32;
+                }
+            }
+            row_first += row_total;
+        }
+    };
+
+    uint32_t hp_prev[J / 2], first_prev = 0, tile_prev = CS_NONE;
+    if (lane == 0 && s_tile[0] != CS_NONE)
+        request_tile(s_tile[0]);
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t tile = s_tile[k % 4];
+        // ticket of iteration k + 2: requested now, published before the barrier
+        uint32_t t2 = 0;
+        if (tid == 0 && tile != CS_NONE)
+            t2 = atomicAdd(ticket, 1u);
+
+        uint32_t hp[J / 2];
+        if (tile != CS_NONE) {
+            const bool full = tile_is_full(tile);
+            mbar_wait(&s_full[warp], k & 1);
+            uint32_t cnt = 0;
+            #pragma unroll
+            for (int q = 0; q < J / 2; ++q) {
+                hp[q] = pack16(fetch_vector(tile, full, 2 * q)) |
+                        (pack16(fetch_vector(tile, full, 2 * q + 1)) << 16);
+                cnt += __popc(hp[q]);
+            }
+            __syncwarp(); // every lane has read the buffer: refill it
+            const uint32_t next = s_tile[(k + 1) % 4];
+            if (lane == 0 && next != CS_NONE)
+                request_tile(next);
+            const uint32_t wtotal = __reduce_add_sync(FULL_MASK, cnt);
+            if (lane == 0)
+                s_wtot[k & 1][warp] = wtotal;
+            if (tid == 0)
+                s_tile[(k + 2) % 4] = t2 < ntiles ? t2 : CS_NONE;
+        }
+        __syncthreads();
+
+        if (tile_prev != CS_NONE)
+            expand(tile_prev, hp_prev, first_prev + s_prefix[(k - 1) & 1]);
+        if (tile == CS_NONE)
+            break;
+
+        uint32_t wexcl = 0;
+        #pragma unroll
+        for (int w = 0; w < CS_WARPS; ++w)
+            wexcl += (uint32_t) w < warp ? s_wtot[k & 1][w] : 0u;
+        #pragma unroll
+        for (int q = 0; q < J / 2; ++q)
+            hp_prev[q] = hp[q];
+        first_prev = wexcl;
+        tile_prev = tile;
+    }
+}
+
+static int compress_stream(cudaStream_t stream, const uint8_t *in, uint64_t size, uint32_t *out,
+                           uint32_t *count_dev) {
+    constexpr int J = 8;
+    constexpr uint32_t TILE = CS_WARPS * J * 512;
+    auto kernel = compress_stream_kernel<J>;
+    const uint32_t mis = (uint32_t) ((uintptr_t) in & 15);
+    const uint32_t ntiles = (uint32_t) ceil_div(size + mis, TILE);
+
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = dev < 64 ? occ_cache[dev].load(std::memory_order_relaxed) : 0;
+    if (occ == 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) TILE));
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CS_THREADS + 32, TILE));
+        occ = occ < 1 ? 1 : occ;
+        if (dev < 64)
+            occ_cache[dev].store(occ, std::memory_order_relaxed);
+    }
+
+    const size_t desc_bytes = (size_t) ntiles * sizeof(uint64_t);
+    void *scratch = temp_alloc(desc_bytes + 16, stream);
+    if (!scratch)
+        return fail(B200_ERR_CUDA, "jit_compress(): out of memory");
+    cudaError_t err = cudaMemsetAsync(scratch, 0, desc_bytes + 16, stream);
+    if (err != cudaSuccess) {
+        temp_free(scratch, stream);
+        return cuda_fail(err, "cudaMemsetAsync");
+    }
+    const uint32_t grid = (uint32_t) std::min<uint64_t>(ntiles, (uint64_t) sm_count() * occ);
+    kernel<<<grid, CS_THREADS + 32, TILE, stream>>>(in, out, size, mis, ntiles, (uint64_t *) scratch,
+                                                 (uint32_t *) ((uint8_t *) scratch + desc_bytes),
+                                                 count_dev);
+    temp_free(scratch, stream);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+/// 1 (default): single-pass stream kernel, 2: bit-packed two-pass path
+/// (development switch, kept for A/B measurements)
+static int compress_path() {
+    static int path = -1;
+    if (path < 0) {
+        const char *s = getenv("B200_COMPRESS_PATH");
+        path = s ? atoi(s) : 1;
+    }
+    return path;
+}
+
 static int compress_two_pass(cudaStream_t stream, const uint8_t *in, uint64_t size, uint32_t *out,
                              uint32_t *count_dev) {
     const uint32_t mis = (uint32_t) ((uintptr_t) in & 15);
@@ -429,7 +759,8 @@ int b200_compress_async(void *stream_, const uint8_t *in, uint64_t size, uint32_
     // small masks: one launch of the single-pass kernel; large ones: two passes
     // over a bit-packed copy of the mask
     if (size > 32768)
-        return compress_two_pass(stream, in, size, out, count_dev);
+        return compress_path() == 2 ? compress_two_pass(stream, in, size, out, count_dev)
+                                    : compress_stream(stream, in, size, out, count_dev);
 
     constexpr int J = 4;
     constexpr uint32_t TILE = COMPRESS_THREADS * J * 16;

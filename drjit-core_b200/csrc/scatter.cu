@@ -10,9 +10,10 @@
 // Modes (jit.h:1017-1066):
 //   Direct       one red.global per element;
 //   Local        lanes that hit the same address are found with match.any and
-//                merged by a rank-halving tree; the lowest lane issues the
-//                single atomic (Auto resolves to this, as in the reference's
-//                default flag set);
+//                merged (butterfly when all 32 agree, else a rank-halving
+//                tree); the lowest lane issues the single atomic;
+//   Auto         Local (as in the reference's default flag set), except that a
+//                warp whose probe batches show no conflicts issues directly;
 //   NoConflicts  plain load / op / store.
 #include "common.cuh"
 
@@ -123,7 +124,50 @@ template <typename T> B200_DEVICE T shfl_elem(uint32_t mask, T v, int src) {
     }
 }
 
-template <typename T, int Op, int MODE>
+/// Warp pre-reduction of the lanes in 'active' that hit the same address
+/// (src/cuda_scatter.cpp:125-244); the lowest lane of every group issues the
+/// single atomic.  Returns the number of lanes that were absorbed by another one.
+template <typename T, int Op>
+B200_DEVICE uint32_t scatter_local(T *target, uint32_t idx, T v, bool on, uint32_t lane) {
+    const uint32_t active = __ballot_sync(FULL_MASK, on);
+    uint32_t absorbed = 0;
+    if (on) {
+        const uint32_t peers = __match_any_sync(active, idx);
+        const uint32_t lower = peers & ((1u << lane) - 1);
+        if (peers == FULL_MASK) {
+            // all 32 lanes hit one address: butterfly
+            #pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+                v = ElemOp<T, Op>::apply(v, shfl_elem<T>(FULL_MASK, v, lane ^ d));
+        } else if (__any_sync(active, peers != (1u << lane))) {
+            // rank-halving tree inside every group of equal addresses: each
+            // round a lane absorbs the next surviving peer above it, then the
+            // odd-ranked lanes drop out
+            uint32_t rank = __popc(lower);
+            uint32_t above = peers & ~((2u << lane) - 1);
+            while (__any_sync(active, above != 0)) {
+                int src = above ? __ffs(above) - 1 : (int) lane;
+                T other = shfl_elem<T>(active, v, src);
+                if (above)
+                    v = ElemOp<T, Op>::apply(v, other);
+                uint32_t even = __ballot_sync(active, (rank & 1) == 0);
+                above &= even;
+                rank >>= 1;
+            }
+        }
+        if (lower == 0) // lowest lane of its group
+            Atomic<T, Op>::apply(target + idx, v);
+        absorbed = __popc(__ballot_sync(active, lower != 0));
+    }
+    return absorbed;
+}
+
+/// MODE: Direct / Local / NoConflicts as in jit.h:1017-1066.  ADAPTIVE (Auto):
+/// Local, except that a warp which finds (almost) no address conflicts in a
+/// probe batch issues the next batches directly -- finding the peers
+/// (match.any over 32 distinct addresses) costs more than the atomics it saves
+/// when indices are incoherent.  Every eighth batch is a probe.
+template <typename T, int Op, int MODE, bool ADAPTIVE, int U>
 __global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                       const uint32_t *__restrict__ index, const uint8_t *__restrict__ mask,
@@ -131,10 +175,11 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
     const uint64_t first = (uint64_t) blockIdx.x * SCATTER_THREADS + threadIdx.x;
-    constexpr int U = 4;
+    bool local = true;   // warp-uniform
+    uint32_t batch = 0;
 
     // all lanes of a warp run the same number of iterations (warp collectives)
-    for (uint64_t base = first - lane; base < n; base += stride * U) {
+    for (uint64_t base = first - lane; base < n; base += stride * U, ++batch) {
         T val[U];
         uint32_t idx[U];
         bool on[U];
@@ -149,6 +194,7 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                     on[u] = __ldcs(mask + i) != 0;
             }
         }
+        const bool probe = ADAPTIVE && (batch & 7) == 0;
         #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (base + (uint64_t) u * stride >= n)
@@ -162,28 +208,12 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                 if (on[u])
                     Atomic<T, Op>::apply(target + idx[u], val[u]);
             } else {
-                uint32_t active = __ballot_sync(FULL_MASK, on[u]);
-                if (on[u]) {
-                    uint32_t peers = __match_any_sync(active, idx[u]);
-                    T v = val[u];
-                    if (__any_sync(active, peers != (1u << lane))) {
-                        // rank-halving tree inside every group of equal addresses:
-                        // each round a lane absorbs the next surviving peer above
-                        // it, then the odd-ranked lanes drop out
-                        uint32_t rank = __popc(peers & ((1u << lane) - 1));
-                        uint32_t above = peers & ~((2u << lane) - 1);
-                        while (__any_sync(active, above != 0)) {
-                            int src = above ? __ffs(above) - 1 : (int) lane;
-                            T other = shfl_elem<T>(active, v, src);
-                            if (above)
-                                v = ElemOp<T, Op>::apply(v, other);
-                            uint32_t even = __ballot_sync(active, (rank & 1) == 0);
-                            above &= even;
-                            rank >>= 1;
-                        }
-                    }
-                    if ((peers & ((1u << lane) - 1)) == 0) // lowest lane of its group
-                        Atomic<T, Op>::apply(target + idx[u], v);
+                if (!ADAPTIVE || local || (probe && u == 0)) {
+                    const uint32_t absorbed = scatter_local<T, Op>(target, idx[u], val[u], on[u], lane);
+                    if (probe && u == 0)
+                        local = __shfl_sync(FULL_MASK, absorbed, __ffs(__ballot_sync(FULL_MASK, on[u]) | 0x80000000u) - 1) >= 4;
+                } else if (on[u]) {
+                    Atomic<T, Op>::apply(target + idx[u], val[u]);
                 }
             }
         }
@@ -201,21 +231,26 @@ struct ScatterCall {
 };
 
 template <typename T, int Op> static int launch_scatter(const ScatterCall &c) {
+    constexpr int U = 4;
     uint32_t grid = (uint32_t) std::max<uint64_t>(
-        1, std::min<uint64_t>(ceil_div(c.n, (uint64_t) SCATTER_THREADS * 4), (uint64_t) sm_count() * 16));
+        1, std::min<uint64_t>(ceil_div(c.n, (uint64_t) SCATTER_THREADS * U), (uint64_t) sm_count() * 16));
     T *target = (T *) c.target;
     const T *value = (const T *) c.value;
     switch (c.mode) {
         case B200_MODE_DIRECT:
-            scatter_reduce_kernel<T, Op, B200_MODE_DIRECT><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+            scatter_reduce_kernel<T, Op, B200_MODE_DIRECT, false, U><<<grid, SCATTER_THREADS, 0, c.stream>>>(
                 target, value, c.index, c.mask, c.n);
             break;
         case B200_MODE_NO_CONFLICTS:
-            scatter_reduce_kernel<T, Op, B200_MODE_NO_CONFLICTS><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+            scatter_reduce_kernel<T, Op, B200_MODE_NO_CONFLICTS, false, U><<<grid, SCATTER_THREADS, 0, c.stream>>>(
                 target, value, c.index, c.mask, c.n);
             break;
-        default:
-            scatter_reduce_kernel<T, Op, B200_MODE_LOCAL><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+        case B200_MODE_LOCAL:
+            scatter_reduce_kernel<T, Op, B200_MODE_LOCAL, false, U><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+                target, value, c.index, c.mask, c.n);
+            break;
+        default: // Auto
+            scatter_reduce_kernel<T, Op, B200_MODE_LOCAL, true, U><<<grid, SCATTER_THREADS, 0, c.stream>>>(
                 target, value, c.index, c.mask, c.n);
             break;
     }
@@ -283,9 +318,7 @@ int b200_scatter_reduce(void *stream_, int vt, int op, int mode, void *target,
                     "jit_var_scatter(): the %s backend does not support the requested type of "
                     "atomic reduction (%s) for variables of type (%s)",
                     "CUDA", op_name(op), type_name(vt));
-    if (mode == B200_MODE_AUTO)
-        mode = B200_MODE_LOCAL;
-    if (mode != B200_MODE_DIRECT && mode != B200_MODE_LOCAL && mode != B200_MODE_NO_CONFLICTS)
+    if (mode != B200_MODE_AUTO && mode != B200_MODE_DIRECT && mode != B200_MODE_LOCAL && mode != B200_MODE_NO_CONFLICTS)
         return fail(B200_ERR_UNSUPPORTED, "jit_var_scatter(): unsupported reduction mode %d", mode);
     if (n == 0)
         return B200_OK;

@@ -215,3 +215,94 @@ class Reference:
 
     def reduce_identity(self, vt, op):
         return self.lib.ref_reduce_identity(vt, op)
+
+
+_REF_CUDA_SO = os.path.join(_HERE, "_ref", "libref_cuda.so")
+
+
+def ref_cuda_available():
+    return os.path.exists(_REF_CUDA_SO)
+
+
+class ReferenceCUDA:
+    """The reference built WITH its CUDA backend (oracle/_ref/libref_cuda.so):
+    its own CUDA kernels (compute_75 PTX, JIT-compiled by the driver) driven
+    through the public jit_* entry points on raw DEVICE pointers (ints, e.g.
+    torch's ``tensor.data_ptr()``).  GPU box only.  All calls are enqueued on
+    the reference's own stream; ``sync()`` waits for it."""
+
+    _instance = None
+
+    @classmethod
+    def get(cls):
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    def __init__(self):
+        if not ref_cuda_available():
+            raise RuntimeError("oracle/_ref/libref_cuda.so has not been built")
+        L = self.lib = ctypes.CDLL(_REF_CUDA_SO)
+        L.refcuda_last_error.restype = ctypes.c_char_p
+        L.refcuda_stream.restype = ctypes.c_void_p
+        vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
+        L.refcuda_block_reduce.argtypes = [i32, i32, u32, u32, vp, vp]
+        L.refcuda_block_prefix_reduce.argtypes = [i32, i32, u32, u32, i32, i32, vp, vp]
+        L.refcuda_reduce_dot.argtypes = [i32, vp, vp, u32, vp]
+        L.refcuda_compress.argtypes = [vp, u32, vp, ctypes.POINTER(u32)]
+        L.refcuda_block_mkperm.argtypes = [vp, u32, u32, u32, vp, vp, ctypes.POINTER(u32)]
+        L.refcuda_scatter_reduce.argtypes = [i32, i32, i32, vp, ctypes.c_size_t, vp, vp, vp,
+                                             ctypes.c_size_t, i32]
+        L.refcuda_all.argtypes = [vp, u32, ctypes.POINTER(i32)]
+        L.refcuda_any.argtypes = [vp, u32, ctypes.POINTER(i32)]
+        L.refcuda_can_scatter_reduce.argtypes = [i32, i32]
+        if L.refcuda_init():
+            raise RuntimeError(L.refcuda_last_error().decode())
+
+    def _check(self, rc):
+        if rc:
+            raise ValueError(self.lib.refcuda_last_error().decode())
+
+    def sync(self):
+        self.lib.refcuda_sync()
+
+    def block_reduce(self, vt, op, size, block_size, d_in, d_out):
+        self._check(self.lib.refcuda_block_reduce(vt, op, size, block_size, d_in, d_out))
+
+    def block_prefix_reduce(self, vt, op, size, block_size, exclusive, reverse, d_in, d_out):
+        self._check(self.lib.refcuda_block_prefix_reduce(vt, op, size, block_size, int(exclusive),
+                                                         int(reverse), d_in, d_out))
+
+    def reduce_dot(self, vt, d_a, d_b, size, d_out):
+        self._check(self.lib.refcuda_reduce_dot(vt, d_a, d_b, size, d_out))
+
+    def compress(self, d_mask, size, d_out):
+        """NOTE: the reference zero-fills the mask buffer past 'size' (up to the
+        next power of two >= size, src/cuda_ts.cpp:708-710,746-748)."""
+        cnt = ctypes.c_uint32(0)
+        self._check(self.lib.refcuda_compress(d_mask, size, d_out, ctypes.byref(cnt)))
+        return cnt.value
+
+    def block_mkperm(self, d_keys, size, block_size, bucket_count, d_perm, h_offsets_pinned):
+        uq = ctypes.c_uint32(0)
+        self._check(self.lib.refcuda_block_mkperm(d_keys, size, block_size, bucket_count, d_perm,
+                                                  h_offsets_pinned, ctypes.byref(uq)))
+        return uq.value
+
+    def scatter_reduce(self, vt, op, mode, d_target, target_size, d_value, d_index, d_mask, n,
+                       repeat=1):
+        self._check(self.lib.refcuda_scatter_reduce(vt, op, mode, d_target, target_size, d_value,
+                                                    d_index, d_mask, n, repeat))
+
+    def can_scatter_reduce(self, vt, op):
+        return bool(self.lib.refcuda_can_scatter_reduce(vt, op))
+
+    def all(self, d_mask, size):
+        r = ctypes.c_int(0)
+        self._check(self.lib.refcuda_all(d_mask, size, ctypes.byref(r)))
+        return bool(r.value)
+
+    def any(self, d_mask, size):
+        r = ctypes.c_int(0)
+        self._check(self.lib.refcuda_any(d_mask, size, ctypes.byref(r)))
+        return bool(r.value)
