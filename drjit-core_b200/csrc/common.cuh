@@ -36,6 +36,8 @@ int ensure_init();
 /// Stream-ordered temporary memory (CUDA memory-pool backed)
 void *temp_alloc(size_t bytes, cudaStream_t stream);
 void temp_free(void *ptr, cudaStream_t stream);
+/// A pinned (device-accessible) host word owned by the calling thread, or NULL
+uint32_t *pinned_scalar();
 
 #define B200_CUDA_CHECK(expr)                                                  \
     do {                                                                       \

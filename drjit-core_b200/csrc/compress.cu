@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "pipeline.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -387,19 +388,30 @@ compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__rest
 //
 // What makes a single pass cheap here is that a packed tile is tiny: a thread
 // reduces its J 16-byte vectors (J * 16 entries) to J 16-bit words kept in J / 2
-// registers, so a CTA can hold TWO tiles at once and run a software pipeline
+// registers, so a CTA can hold THREE tiles at once and run a software pipeline
 // around the one unavoidable latency, the look-back:
 //
-//   iteration k   compute warps: mask of tile k arrives in registers (loads were
-//                 issued an iteration ago) -> pack to bits -> issue the loads of
-//                 tile k + 1 -> publish the warp totals -> barrier -> EXPAND
-//                 TILE k - 1, whose prefix was resolved in the meantime;
-//                 look-back warp: after the same barrier publishes the aggregate
-//                 of tile k, resolves its exclusive prefix over 64-bit
-//                 {status, count} descriptors and leaves it for iteration k + 1.
+//   compute warp, iteration k   its part of the mask of tile k arrives in shared
+//                 memory (bulk copy issued an iteration ago) -> pack to bits ->
+//                 request tile k + 1 -> publish the warp total (mbarrier arrive, no
+//                 wait) -> EXPAND TILE k - 2, whose first output slots were resolved
+//                 in the meantime.  No CTA-wide barrier.
+//   resolve warp  (one extra warp, on its own clock) waits until all 16 warp totals
+//                 of tile k are in, publishes the tile's count as a 64-bit {status,
+//                 count} descriptor, reads the counts of the whole WAVE of tiles
+//                 (below) for the exclusive prefix and hands every compute warp its
+//                 first output slot through a second mbarrier.
 //
-// Persistent CTAs (two per SM), tiles handed out by an atomic ticket two
-// iterations ahead (forward progress of the look-back + load balance).
+// Persistent CTAs, two per SM, all co-resident (cooperative launch): tile k of CTA b
+// is tile k * gridDim + b, i.e. all CTAs work on the same wave of gridDim
+// consecutive tiles.  There is no chained look-back: a CTA reads the counts of ALL
+// tiles of its wave with loads that are in flight together -- one round trip when
+// nobody is late -- and derives its exclusive prefix inside the wave and the wave
+// total, which every CTA accumulates on its own into the base of the next wave.
+// Why: a dependent global load costs ~2.5 us in this kernel (it queues behind
+// 19 MB of bulk copies in flight; phase time line in tools/cs_trace.py).  A
+// decoupled look-back with 32-wide windows needed ~20 such polls per tile, and a
+// version that read the wave in three rounds of loads still 7.5 us per wave.
 //
 // Layout of a tile (virtual bytes, i.e. relative to the 16-byte aligned address
 // in - mis): warp w owns the contiguous bytes [w * J * 512, (w + 1) * J * 512),
@@ -407,32 +419,54 @@ compress_expand_kernel(const uint32_t *__restrict__ bits, const uint32_t *__rest
 // load instruction of a warp reads 512 contiguous bytes.
 //
 // Expansion of a row (512 entries = one 16-bit word per lane):
-//   dense   (> CS_SPARSE set entries): the row is walked two lanes' words at a
-//           time; the words and their output offsets are broadcast, lane i owns
-//           bit i & 15 of word i >> 4 and stores its index at offset + (number of
-//           set bits below it): every store instruction writes one or two
-//           contiguous runs.
-//   sparse  every lane walks the set bits of its own word (a few iterations).
+//   dense   (> CS_SPARSE set entries): every lane appends the indices of its set
+//           bits to a per-warp staging row in shared memory (16 predicated
+//           stores, no popc / shuffle per entry); the row then leaves with ONE
+//           bulk copy shared -> global (cp.async.bulk) for its 16-byte aligned
+//           middle plus at most 3 + 3 scalar stores for the ragged ends.  The
+//           previous version (broadcast word + offset, lane i owns bit i) cost
+//           27 warp instructions per 32 entries and was issue bound (ncu: 70 %
+//           issue active at density 0.5).
+//   sparse  every lane walks the set bits of its own word (a few iterations)
+//           and stores straight to global memory.
 
-static constexpr int CS_THREADS = 512;             // compute threads (+ 32: look-back warp)
+#ifdef B200_CS_TRACE
+// development aid: per-CTA phase time stamps (globaltimer, ns) of warp 0 and of the
+// resolving warp; [cta][iteration][event]
+static constexpr int CST_ITERS = 16, CST_EVENTS = 12;
+__device__ unsigned long long cs_trace[320][CST_ITERS][CST_EVENTS];
+B200_DEVICE unsigned long long cs_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define CS_STAMP(k, e) do { if (lane == 0 && (k) < CST_ITERS) cs_trace[blockIdx.x][k][e] = cs_now(); } while (0)
+#else
+#define CS_STAMP(k, e) do { } while (0)
+#endif
+
+static constexpr int CS_THREADS = 512;             // compute threads (+ 32: resolve warp)
 static constexpr int CS_WARPS = CS_THREADS / 32;
+static constexpr int CS_WAVE_MAX = 320;            // CTAs per wave (10 descriptors per lane)
 static constexpr uint32_t CS_SPARSE = 48;          // set entries per 512-entry row
 static constexpr uint32_t CS_NONE = 0xffffffffu;
+static constexpr uint32_t CS_STAGE = 512 + 4;      // staging words per warp (row + alignment slack)
+static constexpr int CS_RING = 4;                  // look-back hand-over ring (tiles)
 
 template <int J>
 __global__ void __launch_bounds__(CS_THREADS + 32, 2)
 compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t size,
-                       uint32_t mis, uint32_t ntiles, uint64_t *desc, uint32_t *ticket,
-                       uint32_t *count_out) {
+                       uint32_t mis, uint32_t ntiles, uint64_t *desc, uint32_t *count_out) {
     static_assert(J % 2 == 0 && J <= 8, "J 16-bit words are kept in J / 2 registers");
     constexpr uint32_t WARP_BYTES = J * 512;
     constexpr uint32_t TILE = CS_WARPS * WARP_BYTES;
 
-    __shared__ uint32_t s_tile[4];            // tile of iteration k in s_tile[k % 4]
-    __shared__ uint32_t s_wtot[2][CS_WARPS];  // set entries per warp of tile k in [k & 1]
-    __shared__ uint32_t s_prefix[2];          // exclusive prefix of tile k in [k & 1]
-    __shared__ __align__(8) uint64_t s_full[CS_WARPS]; // the warp's part of a tile has landed
-    extern __shared__ __align__(128) uint8_t cs_smem[]; // CS_WARPS * WARP_BYTES
+    __shared__ uint32_t s_wtot[CS_RING][CS_WARPS];  // set entries per warp of tile k in [k % RING]
+    __shared__ uint32_t s_first[CS_RING][CS_WARPS]; // first output slot per warp of tile k
+    __shared__ __align__(8) uint64_t s_full[CS_WARPS];   // the warp's part of a tile has landed
+    __shared__ __align__(8) uint64_t s_tot_bar[CS_RING]; // totals of tile k are complete (16 arrivals)
+    __shared__ __align__(8) uint64_t s_pfx_bar[CS_RING]; // first slots of tile k are resolved
+    extern __shared__ __align__(128) uint8_t cs_smem[];  // CS_WARPS * (WARP_BYTES + CS_STAGE * 4)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *vin = in - mis;
@@ -442,64 +476,100 @@ compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ ou
         #pragma unroll
         for (int w = 0; w < CS_WARPS; ++w)
             mbar_init(&s_full[w], 1);
+        #pragma unroll
+        for (int r = 0; r < CS_RING; ++r) {
+            mbar_init(&s_tot_bar[r], CS_WARPS);
+            mbar_init(&s_pfx_bar[r], 1);
+        }
         mbar_fence_init();
-        const uint32_t t0 = atomicAdd(ticket, 1u), t1 = atomicAdd(ticket, 1u);
-        s_tile[0] = t0 < ntiles ? t0 : CS_NONE;
-        s_tile[1] = t1 < ntiles ? t1 : CS_NONE;
     }
     __syncthreads();
 
-    // ---- look-back warp
+    auto tile_of = [&](uint32_t k) -> uint32_t {
+        const uint64_t t = (uint64_t) k * gridDim.x + blockIdx.x;
+        return t < ntiles ? (uint32_t) t : CS_NONE;
+    };
+
+    // ---- resolve warp
     if (warp == CS_WARPS) {
+        uint32_t base = 0; // total of all earlier waves
         for (uint32_t k = 0;; ++k) {
-            __syncthreads(); // warp totals of tile k are in s_wtot[k & 1]
-            const uint32_t tile = s_tile[k % 4];
+            const uint32_t tile = tile_of(k);
             if (tile == CS_NONE)
                 break;
-            const uint32_t total = __reduce_add_sync(FULL_MASK, lane < CS_WARPS ? s_wtot[k & 1][lane] : 0u);
-            uint32_t prefix = 0;
-            if (tile == 0) {
-                if (lane == 0)
-                    Desc<uint32_t>::publish(desc, 0, DESC_PREFIX, total);
-            } else {
-                if (lane == 0)
-                    Desc<uint32_t>::publish(desc, tile, DESC_AGGREGATE, total);
-                int64_t win = (int64_t) tile - 1;
-                while (true) {
-                    // window of the 32 preceding tiles, lane 0 nearest; only lanes
-                    // whose entry is still INVALID poll again, entries beyond the
-                    // nearest PREFIX are not waited for
-                    const int64_t idx = win - lane;
-                    uint32_t val = 0, st = DESC_PREFIX, pre;
-                    if (idx >= 0)
-                        st = Desc<uint32_t>::observe(desc, (uint32_t) idx, val);
-                    while (true) {
-                        pre = __ballot_sync(FULL_MASK, st == DESC_PREFIX);
-                        uint32_t inv = __ballot_sync(FULL_MASK, st == DESC_INVALID);
-                        if (pre)
-                            inv &= (1u << (__ffs(pre) - 1)) - 1u;
-                        if (!inv)
-                            break;
-                        __nanosleep(64);
-                        if (st == DESC_INVALID)
-                            st = Desc<uint32_t>::observe(desc, (uint32_t) idx, val);
-                    }
-                    if (pre) {
-                        const uint32_t stop = __ffs(pre) - 1;
-                        prefix += __reduce_add_sync(FULL_MASK, lane <= stop ? val : 0u);
-                        break;
-                    }
-                    prefix += __reduce_add_sync(FULL_MASK, val);
-                    win -= 32;
+            const uint32_t slot = k % CS_RING;
+            CS_STAMP(k, 4);
+            mbar_wait(&s_tot_bar[slot], (k / CS_RING) & 1);
+            CS_STAMP(k, 5);
+            const uint32_t mine = lane < CS_WARPS ? s_wtot[slot][lane] : 0u;
+            uint32_t incl = mine;
+            #pragma unroll
+            for (int d = 1; d < CS_WARPS; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+                if (lane >= (uint32_t) d)
+                    incl += up;
+            }
+            const uint32_t total = __shfl_sync(FULL_MASK, incl, CS_WARPS - 1);
+            if (lane == 0)
+                Desc<uint32_t>::publish(desc, tile, DESC_AGGREGATE, total);
+
+            // counts of the whole wave: every load is issued before the first one is
+            // looked at; entries that are not there yet are polled again
+            const uint32_t wave0 = tile - blockIdx.x;               // first tile of the wave
+            const uint32_t wave_n = min(gridDim.x, ntiles - wave0); // tiles in this wave
+            constexpr int NQ = CS_WAVE_MAX / 32;
+            uint32_t val[NQ], st[NQ];
+            #pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const uint32_t j = 32 * q + lane;
+                val[q] = 0;
+                st[q] = DESC_AGGREGATE;
+                if (j < wave_n)
+                    st[q] = Desc<uint32_t>::observe(desc, wave0 + j, val[q]);
+            }
+            uint32_t below = 0, all = 0;
+#ifdef B200_CS_TRACE
+            uint32_t repolls = 0;
+            {
+                uint32_t any = 0;
+                #pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    any |= st[q];
+                if (__any_sync(FULL_MASK, any == 12345u)) // forces the loads to complete
+                    repolls = 1000;
+                CS_STAMP(k, 3);
+            }
+#endif
+            #pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const uint32_t j = 32 * q + lane;
+                while (__any_sync(FULL_MASK, st[q] == DESC_INVALID)) {
+#ifdef B200_CS_TRACE
+                    repolls++;
+#endif
+                    if (st[q] == DESC_INVALID)
+                        st[q] = Desc<uint32_t>::observe(desc, wave0 + j, val[q]);
                 }
-                if (lane == 0)
-                    Desc<uint32_t>::publish(desc, tile, DESC_PREFIX, prefix + total);
+                all += val[q];
+                below += j < blockIdx.x ? val[q] : 0u;
             }
-            if (lane == 0) {
-                s_prefix[k & 1] = prefix;
-                if (tile == ntiles - 1)
-                    *count_out = prefix + total;
-            }
+            all = __reduce_add_sync(FULL_MASK, all);
+            below = __reduce_add_sync(FULL_MASK, below);
+            CS_STAMP(k, 6);
+#ifdef B200_CS_TRACE
+            if (lane == 0 && k < CST_ITERS)
+                cs_trace[blockIdx.x][k][11] = repolls;
+#endif
+            const uint32_t prefix = base + below;
+            base += all;
+            if (lane < CS_WARPS)
+                s_first[slot][lane] = prefix + incl - mine;
+            if (lane == 0 && tile == ntiles - 1)
+                *count_out = prefix + total;
+            __syncwarp();
+            CS_STAMP(k, 7);
+            if (lane == 0)
+                mbar_arrive(&s_pfx_bar[slot]);
         }
         return;
     }
@@ -510,6 +580,7 @@ compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ ou
     // ahead and tracked by the warp's own mbarrier.  Tiles that are not entirely
     // inside the array (a misaligned head, the tail) are read with guarded loads.
     uint4 *wbuf = (uint4 *) cs_smem + (size_t) warp * (WARP_BYTES / 16);
+    uint32_t *stage = (uint32_t *) (cs_smem + (size_t) CS_WARPS * WARP_BYTES) + (size_t) warp * CS_STAGE;
     auto tile_is_full = [&](uint32_t tile) {
         return (uint64_t) tile * TILE >= mis && (uint64_t) (tile + 1) * TILE <= vend;
     };
@@ -541,6 +612,7 @@ compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ ou
 
     // expansion of one tile held as packed bits (hp[q] = word of row 2q | word of
     // row 2q + 1 << 16); 'first' = output slot of the warp's first set entry
+    bool store_pending = false; // a bulk store may still be reading the staging row
     auto expand = [&](uint32_t tile, const uint32_t (&hp)[J / 2], uint32_t first) {
         // inclusive scans over the lanes of all J row counts at once: three
         // 10-bit fields per register (a row holds at most 512 set entries)
@@ -574,7 +646,6 @@ compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ ou
         // entry index of bit 0 of this lane's word of row 0 (may wrap below zero
         // for the masked-out head bytes, which are never set)
         const uint32_t item0 = (uint32_t) ((uint64_t) tile * TILE + warp * WARP_BYTES + lane * 16 - mis);
-        const uint32_t sub = lane & 15, below = (1u << sub) - 1u;
         uint32_t row_first = first;
         #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -583,47 +654,75 @@ compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ ou
                 continue; // warp-uniform
             const uint32_t incl = (P[j / 3] >> (10 * (j % 3))) & 0x3ffu;
             uint32_t word = (hp[j / 2] >> (16 * (j & 1))) & 0xffffu;
-            uint32_t o = row_first + incl - c[j]; // slot of this lane's first set entry
+            const uint32_t item = item0 + j * 512;
             if (row_total <= CS_SPARSE) {
-                uint32_t item = item0 + j * 512;
+                uint32_t o = row_first + incl - c[j]; // slot of this lane's first set entry
                 while (word) {
                     const uint32_t b = __ffs(word) - 1;
                     word &= word - 1;
                     out[o++] = item + b;
                 }
             } else {
-                const uint32_t nz = __ballot_sync(FULL_MASK, word != 0);
-                // item of bit 'sub' of the word of lane (lane >> 4)
-                const uint32_t item = item0 - lane * 16 + j * 512 + (lane >> 4) * 16 + sub;
-                #pragma unroll 4
-                for (uint32_t s = 0; s < 16; ++s) {
-                    if (((nz >> (2 * s)) & 3u) == 0)
-                        continue; // warp-uniform
-                    const uint32_t src = 2 * s + (lane >> 4);
-                    const uint32_t w = __shfl_sync(FULL_MASK, word, src);
-                    const uint32_t wo = __shfl_sync(FULL_MASK, o, src);
-                    if ((w >> sub) & 1u)
-                        out[wo + __popc(w & below)] = item + s * 32;
+                // stage[a + i] <-> out[row_first + i]: 'a' makes 16-byte aligned
+                // staging words coincide with 16-byte aligned global addresses
+                uint32_t *dst = out + row_first;
+                const uint32_t a = (uint32_t) (((uintptr_t) dst >> 2) & 3u);
+                if (store_pending) {
+                    if (lane == 0)
+                        bulk_wait_read<0>();
+                    __syncwarp();
+                }
+                uint32_t *sp = stage + a + (incl - c[j]);
+                #pragma unroll
+                for (int b = 0; b < 16; ++b) {
+                    if (word & (1u << b))
+                        *sp++ = item + b;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                const uint32_t end = a + row_total;           // staging words [a, end) are valid
+                const uint32_t lo = (a + 3u) & ~3u, hi = end & ~3u;
+                if (hi > lo) {
+                    if (lane == 0) {
+                        bulk_s2g(dst - a + lo, stage + lo, (hi - lo) * 4);
+                        bulk_commit();
+                    }
+                    store_pending = true;
+                    // ragged ends: [a, lo) and [hi, end)
+                    if (lane < lo - a)
+                        dst[lane] = stage[a + lane];
+                    else if (lane >= 4 && lane - 4 < end - hi)
+                        dst[hi - a + lane - 4] = stage[hi + lane - 4];
+                } else {
+                    // fewer than one aligned vector (cannot happen for dense rows,
+                    // kept for safety)
+                    for (uint32_t i = lane; i < row_total; i += 32)
+                        dst[i] = stage[a + i];
+                    __syncwarp();
                 }
             }
             row_first += row_total;
         }
     };
 
-    uint32_t hp_prev[J / 2], first_prev = 0, tile_prev = CS_NONE;
-    if (lane == 0 && s_tile[0] != CS_NONE)
-        request_tile(s_tile[0]);
+    // tiles k - 1 and k - 2 wait for their prefix as packed bits in registers
+    uint32_t hp1[J / 2], hp2[J / 2], tile1 = CS_NONE, tile2 = CS_NONE;
+    #pragma unroll
+    for (int q = 0; q < J / 2; ++q)
+        hp1[q] = hp2[q] = 0;
+    if (lane == 0 && tile_of(0) != CS_NONE)
+        request_tile(tile_of(0));
     for (uint32_t k = 0;; ++k) {
-        const uint32_t tile = s_tile[k % 4];
-        // ticket of iteration k + 2: requested now, published before the barrier
-        uint32_t t2 = 0;
-        if (tid == 0 && tile != CS_NONE)
-            t2 = atomicAdd(ticket, 1u);
-
+        const uint32_t tile = tile_of(k);
         uint32_t hp[J / 2];
+        #pragma unroll
+        for (int q = 0; q < J / 2; ++q)
+            hp[q] = 0;
         if (tile != CS_NONE) {
             const bool full = tile_is_full(tile);
+            if (warp == 0) CS_STAMP(k, 0);
             mbar_wait(&s_full[warp], k & 1);
+            if (warp == 0) CS_STAMP(k, 1);
             uint32_t cnt = 0;
             #pragma unroll
             for (int q = 0; q < J / 2; ++q) {
@@ -632,69 +731,89 @@ compress_stream_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ ou
                 cnt += __popc(hp[q]);
             }
             __syncwarp(); // every lane has read the buffer: refill it
-            const uint32_t next = s_tile[(k + 1) % 4];
+            const uint32_t next = tile_of(k + 1);
             if (lane == 0 && next != CS_NONE)
                 request_tile(next);
             const uint32_t wtotal = __reduce_add_sync(FULL_MASK, cnt);
-            if (lane == 0)
-                s_wtot[k & 1][warp] = wtotal;
-            if (tid == 0)
-                s_tile[(k + 2) % 4] = t2 < ntiles ? t2 : CS_NONE;
+            if (lane == 0) {
+                // slot k % RING was last read for tile k - RING, which every warp
+                // has expanded (it waited for that tile's prefix two iterations ago)
+                s_wtot[k % CS_RING][warp] = wtotal;
+                mbar_arrive(&s_tot_bar[k % CS_RING]);
+            }
+            if (warp == 0) CS_STAMP(k, 2);
         }
-        __syncthreads();
-
-        if (tile_prev != CS_NONE)
-            expand(tile_prev, hp_prev, first_prev + s_prefix[(k - 1) & 1]);
-        if (tile == CS_NONE)
+        if (tile2 != CS_NONE) {
+            const uint32_t slot = (k - 2) % CS_RING;
+            if (warp == 0) CS_STAMP(k, 8);
+            mbar_wait(&s_pfx_bar[slot], ((k - 2) / CS_RING) & 1);
+            if (warp == 0) CS_STAMP(k, 9);
+            expand(tile2, hp2, s_first[slot][warp]);
+            if (warp == 0) CS_STAMP(k, 10);
+        }
+        if (tile == CS_NONE && tile1 == CS_NONE)
             break;
-
-        uint32_t wexcl = 0;
         #pragma unroll
-        for (int w = 0; w < CS_WARPS; ++w)
-            wexcl += (uint32_t) w < warp ? s_wtot[k & 1][w] : 0u;
-        #pragma unroll
-        for (int q = 0; q < J / 2; ++q)
-            hp_prev[q] = hp[q];
-        first_prev = wexcl;
-        tile_prev = tile;
+        for (int q = 0; q < J / 2; ++q) {
+            hp2[q] = hp1[q];
+            hp1[q] = hp[q];
+        }
+        tile2 = tile1;
+        tile1 = tile;
     }
+    // the staging row must outlive the last bulk store that reads it
+    if (store_pending && lane == 0)
+        bulk_wait_read<0>();
 }
+
+static int compress_two_pass(cudaStream_t stream, const uint8_t *in, uint64_t size, uint32_t *out,
+                             uint32_t *count_dev);
 
 static int compress_stream(cudaStream_t stream, const uint8_t *in, uint64_t size, uint32_t *out,
                            uint32_t *count_dev) {
     constexpr int J = 8;
     constexpr uint32_t TILE = CS_WARPS * J * 512;
+    constexpr size_t smem = TILE + (size_t) CS_WARPS * CS_STAGE * 4;
     auto kernel = compress_stream_kernel<J>;
-    const uint32_t mis = (uint32_t) ((uintptr_t) in & 15);
-    const uint32_t ntiles = (uint32_t) ceil_div(size + mis, TILE);
+    uint32_t mis = (uint32_t) ((uintptr_t) in & 15);
+    uint32_t ntiles = (uint32_t) ceil_div(size + mis, TILE);
 
+    // co-residency of all CTAs is what guarantees forward progress of the look-back:
+    // cooperative launch, grid <= what fits; without support for it, two passes
     static std::atomic<int> occ_cache[64];
     int dev = 0;
     cudaGetDevice(&dev);
     int occ = dev < 64 ? occ_cache[dev].load(std::memory_order_relaxed) : 0;
     if (occ == 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) TILE));
-        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CS_THREADS + 32, TILE));
-        occ = occ < 1 ? 1 : occ;
+        int coop = 0;
+        B200_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CS_THREADS + 32, smem));
+        occ = coop && occ >= 1 ? occ : -1;
         if (dev < 64)
             occ_cache[dev].store(occ, std::memory_order_relaxed);
     }
+    if (occ < 0)
+        return compress_two_pass(stream, in, size, out, count_dev);
 
     const size_t desc_bytes = (size_t) ntiles * sizeof(uint64_t);
-    void *scratch = temp_alloc(desc_bytes + 16, stream);
-    if (!scratch)
+    uint64_t *desc = (uint64_t *) temp_alloc(desc_bytes, stream);
+    if (!desc)
         return fail(B200_ERR_CUDA, "jit_compress(): out of memory");
-    cudaError_t err = cudaMemsetAsync(scratch, 0, desc_bytes + 16, stream);
+    cudaError_t err = cudaMemsetAsync(desc, 0, desc_bytes, stream);
     if (err != cudaSuccess) {
-        temp_free(scratch, stream);
+        temp_free(desc, stream);
         return cuda_fail(err, "cudaMemsetAsync");
     }
-    const uint32_t grid = (uint32_t) std::min<uint64_t>(ntiles, (uint64_t) sm_count() * occ);
-    kernel<<<grid, CS_THREADS + 32, TILE, stream>>>(in, out, size, mis, ntiles, (uint64_t *) scratch,
-                                                 (uint32_t *) ((uint8_t *) scratch + desc_bytes),
-                                                 count_dev);
-    temp_free(scratch, stream);
-    B200_LAUNCH_CHECK();
+    const uint32_t grid = (uint32_t) std::min<uint64_t>(
+        std::min<uint64_t>(ntiles, (uint64_t) sm_count() * occ), CS_WAVE_MAX);
+    void *args[] = { (void *) &in, (void *) &out, (void *) &size, (void *) &mis, (void *) &ntiles,
+                     (void *) &desc, (void *) &count_dev };
+    err = cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(CS_THREADS + 32), args, smem, stream);
+    temp_free(desc, stream);
+    if (err != cudaSuccess)
+        return cuda_fail(err, "cudaLaunchCooperativeKernel(compress_stream_kernel)");
+    count_launch();
     return B200_OK;
 }
 
@@ -744,6 +863,12 @@ using namespace b200;
 
 extern "C" {
 
+#ifdef B200_CS_TRACE
+__attribute__((visibility("default"))) int b200_debug_cs_trace(void *dst, size_t bytes) {
+    return (int) cudaMemcpyFromSymbol(dst, cs_trace, std::min(bytes, sizeof(cs_trace)));
+}
+#endif
+
 int b200_compress_async(void *stream_, const uint8_t *in, uint64_t size, uint32_t *out,
                         uint32_t *count_dev) {
     int rc = ensure_init();
@@ -789,22 +914,16 @@ int b200_compress(void *stream_, const uint8_t *in, uint64_t size, uint32_t *out
         return B200_OK;
     }
     cudaStream_t stream = resolve_stream(stream_);
-    uint32_t *count_dev = (uint32_t *) temp_alloc(sizeof(uint32_t), stream);
-    if (!count_dev)
-        return fail(B200_ERR_CUDA, "jit_compress(): out of memory");
-    rc = b200_compress_async(stream, in, size, out, count_dev);
-    if (rc) {
-        temp_free(count_dev, stream);
-        return rc;
-    }
     // the reference reads the count from pinned memory after a full stream
-    // synchronisation (src/cuda_ts.cpp:759-762)
-    cudaError_t err = cudaMemcpyAsync(count, count_dev, sizeof(uint32_t),
-                                      cudaMemcpyDeviceToHost, stream);
-    temp_free(count_dev, stream);
-    if (err != cudaSuccess)
-        return cuda_fail(err, "cudaMemcpyAsync");
+    // synchronisation (src/cuda_ts.cpp:759-762); here the kernel writes it there
+    uint32_t *count_pinned = pinned_scalar();
+    if (!count_pinned)
+        return fail(B200_ERR_CUDA, "jit_compress(): could not allocate pinned memory");
+    rc = b200_compress_async(stream, in, size, out, count_pinned);
+    if (rc)
+        return rc;
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *count = *count_pinned;
     return B200_OK;
 }
 

@@ -26,6 +26,10 @@
 //   offsets  non-empty buckets are emitted as (id, start, size, 0) records in
 //            ascending id order by a single-CTA compaction.
 #include "common.cuh"
+#include "pipeline.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -163,11 +167,13 @@ mkperm_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restric
     }
 }
 
-/// Whole-array histogram with a per-CTA shared-memory table that is flushed
-/// with global atomics (bins * 4 bytes must fit the dynamic shared memory).
+/// Whole-array histogram of the keys in [lo, lo + bins) with a per-CTA
+/// shared-memory table that is flushed with global atomics (bins * 4 bytes must
+/// fit the dynamic shared memory).  Keys >= limit count as limit - 1 (out-of-range
+/// keys must not corrupt memory); keys outside the sub-range are skipped.
 __global__ void __launch_bounds__(1024)
-histogram_smem_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32_t bins,
-                      uint32_t *__restrict__ hist) {
+histogram_smem_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32_t lo, uint32_t bins,
+                      uint32_t limit, uint32_t *__restrict__ hist) {
     extern __shared__ uint32_t mk_smem[];
     for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
         mk_smem[b] = 0;
@@ -175,26 +181,34 @@ histogram_smem_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32_t
     uint64_t chunk = (size + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + 3) & ~3ull;
     uint64_t start = min((uint64_t) blockIdx.x * chunk, size), end = min(start + chunk, size);
+    auto add = [&](uint32_t k) {
+        const uint32_t b = min(k, limit - 1) - lo; // wraps for keys below lo
+        if (b < bins)
+            atomicAdd(&mk_smem[b], 1u);
+    };
     bool aligned = ((uintptr_t) keys & 15) == 0;
     if (aligned) {
         uint64_t nvec = (end - start) / 4;
         const uint4 *v = (const uint4 *) (keys + start);
-        for (uint64_t q = threadIdx.x; q < nvec; q += blockDim.x) {
+        uint64_t q = threadIdx.x;
+        for (; q + blockDim.x < nvec; q += 2 * blockDim.x) {
+            uint4 k4 = ld_stream(v + q), k5 = ld_stream(v + q + blockDim.x);
+            add(k4.x); add(k4.y); add(k4.z); add(k4.w);
+            add(k5.x); add(k5.y); add(k5.z); add(k5.w);
+        }
+        for (; q < nvec; q += blockDim.x) {
             uint4 k4 = ld_stream(v + q);
-            atomicAdd(&mk_smem[min(k4.x, bins - 1)], 1u);
-            atomicAdd(&mk_smem[min(k4.y, bins - 1)], 1u);
-            atomicAdd(&mk_smem[min(k4.z, bins - 1)], 1u);
-            atomicAdd(&mk_smem[min(k4.w, bins - 1)], 1u);
+            add(k4.x); add(k4.y); add(k4.z); add(k4.w);
         }
         start += nvec * 4;
     }
     for (uint64_t k = start + threadIdx.x; k < end; k += blockDim.x)
-        atomicAdd(&mk_smem[min(keys[k], bins - 1)], 1u);
+        add(keys[k]);
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) {
         uint32_t c = mk_smem[b];
         if (c)
-            atomicAdd(&hist[b], c);
+            atomicAdd(&hist[lo + b], c);
     }
 }
 
@@ -259,23 +273,20 @@ mkperm_offsets_kernel(const uint32_t *__restrict__ starts, uint64_t stride, uint
 // ------------------------------------------------ single sorting group: tiles
 //
 // block_size == size (what vectorised method dispatch passes): the array is cut
-// into tiles of 8192 keys, one CTA per tile.
+// into tiles of 8192 keys.
 //   tile_hist   per-tile digit counts, written digit-major (table[d][tile]) so
 //               that ONE exclusive scan of the flattened table (scan_fast.cu)
 //               yields the first output slot of every (digit, tile) pair;
-//   tile_place  re-reads the tile, ranks its keys stably (a warp walks its 512
-//               keys in index order, 32 per step: match.any groups equal digits,
-//               the lowest lane advances the warp's private counter), sorts the
-//               tile by digit in shared memory and writes every digit's run with
-//               contiguous stores.  The per-row variant above has every warp
+//   rank_place  re-reads the tile, ranks its keys stably, sorts the tile by digit
+//               in shared memory and writes every digit's run with a bulk copy
+//               (further down).  The per-row variant above has every warp
 //               trickle single elements into `bins` output streams at once,
 //               which thrashes L2 (measured on B200: 6.5x DRAM write
 //               amplification, 2-4 ms for 2^26 keys).
 static constexpr int MT_THREADS = 512;
-static constexpr int MT_WARPS = MT_THREADS / 32;
 static constexpr int MT_ITEMS = 16;
 static constexpr uint32_t MT_TILE = MT_THREADS * MT_ITEMS; // 8192 keys
-static constexpr uint32_t MT_MAX_BINS = 1024;              // 10-bit digits
+static constexpr uint32_t MT_MAX_BINS = 64;                // 6-bit digits
 
 B200_DEVICE uint32_t mt_digit(uint32_t key, uint32_t shift, uint32_t mask, uint32_t bins) {
     return min((key >> shift) & mask, bins - 1); // out-of-range keys must not corrupt memory
@@ -345,161 +356,365 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32
     }
 }
 
-/// 'table' holds the exclusively scanned counts.  The element moved is
-/// idx_in[g] (PAIRS) or the key's own index g; keys_out (optional) receives the
-/// key at the same slot for the next digit pass.
-/// Dynamic shared memory: 2 * MT_TILE + bins words, then MT_WARPS * (bins + 2)
-/// 16-bit counters.
-template <bool PAIRS>
-__global__ void __launch_bounds__(MT_THREADS, 2)
-mkperm_tile_place_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ idx_in,
-                         const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
-                         uint32_t shift, uint32_t mask, uint32_t bins,
-                         uint32_t *__restrict__ perm_out, uint32_t *__restrict__ keys_out) {
-    extern __shared__ uint32_t mk_smem[];
-    uint32_t *s_key = mk_smem;
-    uint32_t *s_idx = mk_smem + MT_TILE;
-    uint32_t *s_delta = mk_smem + 2 * MT_TILE;
-    uint16_t *s_hist = (uint16_t *) (mk_smem + 2 * MT_TILE + bins);
-    // 16-bit counters, two per word; + sentinel bin for the lanes past the end
-    const uint32_t hstride = (bins + 3) & ~1u;
-    __shared__ uint32_t s_warp[MT_WARPS];
+// ------------------------------------------- single sorting group: ranked tiles
+//
+// match.any costs 256 issue cycles per warp instruction on B200 whenever the lanes
+// disagree (tools/ubench_warp_ops.cu; a shuffle: 5, a private LDS + STS pair:
+// 10), so the tile placement above is bound by its 16 match.any per thread.  The
+// kernels below rank WITHOUT any warp-wide matching, the way block radix ranking
+// is classically done:
+//   - a thread owns 16 CONSECUTIVE keys of the tile (blocked arrangement) and a
+//     private column of 16-bit counters, one per digit: rank of a key among the
+//     thread's keys = counter value before the increment (plain LDS / STS);
+//   - two counters (digit d and d + NB / 2) share a 32-bit word, the words are laid
+//     out digit-major / thread-minor, so ONE packed block-wide exclusive scan of
+//     NB / 2 * 512 words gives every (digit, thread) its first slot in the sorted
+//     tile (the low halves' total is added to the high halves afterwards);
+//   - counters cost shared memory per digit AND thread, which limits a pass to
+//     6-bit digits (64 bins): more buckets are sorted least-significant digit
+//     first in ceil(bits / 6) stable passes.  Between passes an element travels as
+//     ONE 32-bit word (remaining key bits << index bits | index) as soon as that
+//     fits, else as a (key, index) pair.
+// The permutation is stable for every bucket count.
+static constexpr int RK_THREADS = 512;                     // (256-thread tiles, 4 per SM, measured no faster)
+static constexpr int RK_ITEMS = 16;
+static constexpr int RK_CTAS = 2;                          // resident CTAs per SM
+static constexpr uint32_t RK_TILE = RK_THREADS * RK_ITEMS; // 8192 keys = MT_TILE
+static_assert(RK_TILE == MT_TILE, "the tile histogram kernel is shared");
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t tile = blockIdx.x;
-    const uint64_t base = (uint64_t) tile * MT_TILE;
+enum { RK_RAW1 = 0,   // keys = the caller's values, the only pass (-> RK_FINAL)
+       RK_RAW = 1,    // keys = the caller's values, first of several passes
+       RK_PAIRS = 2,  // (key, index) pairs
+       RK_PACKED = 3  // one word: remaining key bits << ib | index
+};
+enum { RK_FINAL = 0, RK_OUT_PAIRS = 1, RK_OUT_PACKED = 2 };
 
-    for (uint32_t i = tid; i < MT_WARPS * hstride / 2; i += MT_THREADS)
-        ((uint32_t *) s_hist)[i] = 0;
+static constexpr uint32_t RK_PAD = 8;  // staging slack per run (alignment)
 
-    // ---- load: warp w owns keys [w * 512, (w + 1) * 512) of the tile, striped
-    uint32_t key[MT_ITEMS];
-    #pragma unroll
-    for (int i = 0; i < MT_ITEMS; ++i) {
-        const uint64_t g = base + warp * 512 + i * 32 + lane;
-        key[i] = g < size ? __ldg(keys + g) : 0u;
-    }
-    // first output slot of this thread's digits in this tile (used much later)
-    const uint32_t dpt = (bins + MT_THREADS - 1) / MT_THREADS; // digits per thread (<= 2)
-    const uint32_t d0 = tid * dpt;
-    uint32_t gstart[2] = { 0, 0 };
-    #pragma unroll
-    for (uint32_t q = 0; q < 2; ++q)
-        if (q < dpt && d0 + q < bins)
-            gstart[q] = __ldg(table + (uint64_t) (d0 + q) * ntiles + tile);
-    __syncthreads();
-
-    // ---- stable rank of every key among the warp's keys with the same digit:
-    // match.any groups the lanes with equal digits, the lowest lane of a group
-    // advances the warp's private counter, everyone takes counter + (number of
-    // group members below it).  (A variant that batches the 16 match / atomic /
-    // shuffle steps to break the dependency chain measured 20 % slower: more
-    // live registers than the 64 that two CTAs per SM allow.)
-    uint32_t rank2[MT_ITEMS / 2]; // two 16-bit ranks per register (a rank is < 512)
-    #pragma unroll
-    for (int i = 0; i < MT_ITEMS / 2; ++i)
-        rank2[i] = 0;
-    {
-        uint16_t *whr = s_hist + warp * hstride;
-        #pragma unroll
-        for (int i = 0; i < MT_ITEMS; ++i) {
-            const uint64_t g = base + warp * 512 + i * 32 + lane;
-            const uint32_t d = g < size ? mt_digit(key[i], shift, mask, bins) : bins;
-            const uint32_t peers = __match_any_sync(FULL_MASK, d);
-            const uint32_t below = __popc(peers & lt_mask);
-            uint32_t old = 0;
-            if (below == 0) {
-                old = whr[d];
-                whr[d] = (uint16_t) (old + __popc(peers));
-            }
-            old = __shfl_sync(FULL_MASK, old, __ffs(peers) - 1);
-            rank2[i / 2] |= (old + below) << (16 * (i & 1));
-        }
-    }
-    uint16_t *wh = s_hist + warp * hstride;
-    __syncthreads();
-
-    // ---- per digit: total over the warps, exclusive prefix over the digits,
-    // then every warp's first slot of the digit in the sorted tile
-    uint32_t cnt0 = 0, cnt1 = 0;
-    if (d0 < bins) {
-        #pragma unroll
-        for (int w = 0; w < MT_WARPS; ++w)
-            cnt0 += s_hist[w * hstride + d0];
-    }
-    if (dpt > 1 && d0 + 1 < bins) {
-        #pragma unroll
-        for (int w = 0; w < MT_WARPS; ++w)
-            cnt1 += s_hist[w * hstride + d0 + 1];
-    }
-    const uint32_t mine = cnt0 + cnt1;
-    uint32_t incl = mine;
-    #pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-        const uint32_t up = __shfl_up_sync(FULL_MASK, incl, s);
-        if (lane >= (uint32_t) s)
-            incl += up;
-    }
-    if (lane == 31)
-        s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t lstart = incl - mine; // first slot of digit d0 in the sorted tile
-    #pragma unroll
-    for (int w = 0; w < MT_WARPS; ++w)
-        lstart += (uint32_t) w < warp ? s_warp[w] : 0u;
-    #pragma unroll
-    for (uint32_t q = 0; q < 2; ++q) {
-        const uint32_t d = d0 + q;
-        if (q < dpt && d < bins) {
-            // sorted-tile slot j of this digit goes to global slot j + delta
-            s_delta[d] = gstart[q] - lstart;
-            uint32_t run = lstart;
-            #pragma unroll 4
-            for (int w = 0; w < MT_WARPS; ++w) {
-                const uint32_t t = s_hist[w * hstride + d];
-                s_hist[w * hstride + d] = (uint16_t) run;
-                run += t;
-            }
-            lstart = run;
-        }
-    }
-    __syncthreads();
-
-    // ---- sort the tile by digit in shared memory
-    #pragma unroll
-    for (int i = 0; i < MT_ITEMS; ++i) {
-        const uint64_t g = base + warp * 512 + i * 32 + lane;
-        if (g < size) {
-            const uint32_t d = mt_digit(key[i], shift, mask, bins);
-            const uint32_t slot = wh[d] + ((rank2[i / 2] >> (16 * (i & 1))) & 0xffffu);
-            s_key[slot] = key[i];
-            s_idx[slot] = PAIRS ? __ldg(idx_in + g) : (uint32_t) g;
-        }
-    }
-    __syncthreads();
-
-    // ---- write every digit's run with contiguous stores
-    const uint32_t tile_count = (uint32_t) min((uint64_t) MT_TILE, size - base);
-    for (uint32_t j = tid; j < tile_count; j += MT_THREADS) {
-        const uint32_t k = s_key[j];
-        const uint32_t pos = j + s_delta[mt_digit(k, shift, mask, bins)];
-        perm_out[pos] = s_idx[j];
-        if (keys_out)
-            keys_out[pos] = k;
-    }
+template <int BITS> constexpr uint32_t rk_stage_words() { return RK_TILE + RK_PAD * 2 * (1u << BITS); }
+template <int BITS> constexpr size_t rk_smem_bytes() {
+    // packed counters + sorted tile + per-run {shift, start, count, global start}
+    return (size_t) ((1u << BITS) * (RK_THREADS / 2) + rk_stage_words<BITS>() + 4 * 2 * (1u << BITS)) * 4;
 }
 
-static size_t tile_place_smem(uint32_t bins) {
-    return (size_t) (2 * MT_TILE + bins) * 4 + (size_t) MT_WARPS * ((bins + 3) & ~1u) * 2;
+/// in0 / in1: keys (RAW*, PAIRS) or packed words (PACKED) / indices (PAIRS).
+/// digit = min((x >> shift) & mask, bins - 1) with x the key or the packed word.
+/// out0 / out1: permutation (FINAL), keys / indices (PAIRS), packed words (PACKED).
+/// ib: index bits of a packed word, keymask: the valid key bits.
+///
+/// Counters: the 16-bit counter of (digit d, thread t) lives in 32-bit word
+/// d * 256 + (t % 256), low half for t < 256, high half for t >= 256 -- so that the
+/// counter address is ONE multiply-add away from the digit, and one packed scan
+/// over the words in (digit, column) order ranks the keys of the lower and of the
+/// upper 256 threads at once.  The sorted tile therefore consists of 2 * bins runs
+/// (lower-half threads: digits 0 .. bins - 1, then the upper-half threads); the two
+/// runs of a digit are adjacent in the OUTPUT, where only the order matters.
+///
+/// Every run is staged in shared memory so that its 16-byte aligned part coincides
+/// with 16-byte aligned global addresses and leaves with ONE bulk copy shared ->
+/// global (cp.async.bulk) plus at most 3 + 3 scalar stores for its ragged ends --
+/// there is no per-element store loop.
+template <int BITS, int IN, int OUT, bool FULL>
+B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
+                         const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
+                         uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
+                         uint32_t ahead_tiles, uint32_t *__restrict__ out0, uint32_t *__restrict__ out1,
+                         uint32_t *rk_smem) {
+    constexpr uint32_t NB = 1u << BITS, WPT = NB / 2, G = WPT / 4, HALF = RK_THREADS / 2;
+    constexpr uint32_t ROTM = G < HALF / 32 ? G : HALF / 32; // distinct rotations (see below)
+    uint32_t *s_cnt = rk_smem;                              // NB * 256 packed counters
+    uint32_t *s_stage = rk_smem + NB * HALF;                // sorted tile (+ alignment slack)
+    uint32_t *s_shift = s_stage + rk_stage_words<BITS>();   // staging slot - sorted-tile slot, per run
+    uint32_t *s_pos = s_shift + 2 * NB;                     // staging slot of the run
+    uint32_t *s_len = s_pos + 2 * NB;                       // length of the run
+    uint32_t *s_gpos = s_len + 2 * NB;                      // first global slot of the run
+    __shared__ uint32_t s_warp[RK_THREADS / 32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t base = (uint64_t) tile * RK_TILE;
+    const uint32_t tile_count = FULL ? RK_TILE : (uint32_t) (size - base);
+    const uint32_t first = tid * RK_ITEMS; // tile-local index of the thread's first key
+
+    #pragma unroll
+    for (uint32_t j = 0; j < G; ++j)
+        ((uint4 *) s_cnt)[j * RK_THREADS + tid] = make_uint4(0, 0, 0, 0);
+
+    // ---- load (blocked: 64 contiguous bytes per thread)
+    uint32_t key[RK_ITEMS];
+    auto load16 = [&](const uint32_t *src, uint32_t (&dst)[RK_ITEMS]) {
+        if (FULL && ((uintptr_t) src & 15) == 0) {
+            const uint4 *v = (const uint4 *) (src + base) + tid * (RK_ITEMS / 4);
+            #pragma unroll
+            for (int q = 0; q < RK_ITEMS / 4; ++q) {
+                const uint4 k4 = __ldg(v + q);
+                dst[4 * q] = k4.x; dst[4 * q + 1] = k4.y; dst[4 * q + 2] = k4.z; dst[4 * q + 3] = k4.w;
+            }
+        } else {
+            #pragma unroll
+            for (int i = 0; i < RK_ITEMS; ++i)
+                dst[i] = first + i < tile_count ? __ldg(src + base + first + i) : 0u;
+        }
+    };
+    load16(in0, key);
+    // a CTA that starts once this one has retired finds its keys in L2
+    {
+        const uint64_t ahead = base + (uint64_t) ahead_tiles * RK_TILE + first;
+        if (ahead + RK_ITEMS <= size) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(in0 + ahead));
+            if constexpr (IN == RK_PAIRS)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(in1 + ahead));
+        }
+    }
+    // first output slot of this tile's keys with digit (tid % bins): run tid
+    uint32_t gstart = 0;
+    if (tid < 2 * bins)
+        gstart = __ldg(table + (uint64_t) (tid < bins ? tid : tid - bins) * ntiles + tile);
+
+    // The scan below has thread t' rake the WPT consecutive words [t' * WPT, (t' + 1)
+    // * WPT) with 128-bit accesses; rotating the 16-byte groups of a thread's segment
+    // by rot(t') = (t' * G / 8) % ROTM makes those accesses bank-conflict free (2-way
+    // for 6-bit digits).  For the counting accesses the rotation is the same for all
+    // lanes of a warp and for every digit, i.e. it is a fixed permutation of the
+    // thread's column.
+    const uint32_t col = tid & (HALF - 1);
+    const uint32_t pcol = (col & ~(WPT - 1)) | (((((col % WPT) >> 2) + (col >> 5) % ROTM) % G) << 2) | (col & 3);
+    uint8_t *cnt_mine = (uint8_t *) s_cnt + pcol * 4 + (tid / HALF) * 2;
+    auto digit = [&](uint32_t x) -> uint32_t {
+        if constexpr (IN == RK_RAW1)
+            return min(x, bins - 1);
+        else
+            return min((x >> shift) & mask, bins - 1);
+    };
+    __syncthreads();
+
+    // ---- rank among the thread's own keys (4 bits each)
+    uint32_t lr[2] = { 0, 0 };
+    #pragma unroll
+    for (int i = 0; i < RK_ITEMS; ++i) {
+        if (FULL || first + i < tile_count) {
+            uint16_t *c = (uint16_t *) (cnt_mine + digit(key[i]) * (HALF * 4));
+            const uint32_t v = *c;
+            *c = (uint16_t) (v + 1);
+            lr[i / 8] |= v << (4 * (i & 7));
+        }
+    }
+    __syncthreads();
+
+    // ---- packed exclusive scan of the counters (digit-major, column-minor)
+    {
+        const uint32_t rot = (tid * G / 8) % ROTM;
+        uint4 *seg = (uint4 *) s_cnt + tid * G;
+        uint32_t mine = 0;
+        #pragma unroll
+        for (uint32_t j = 0; j < G; ++j) {
+            const uint4 v = seg[(j + rot) % G];
+            mine += v.x + v.y + v.z + v.w;
+        }
+        uint32_t incl = mine;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= (uint32_t) d)
+                incl += up;
+        }
+        if (lane == 31)
+            s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - mine, total = 0;
+        #pragma unroll
+        for (int w = 0; w < RK_THREADS / 32; ++w) {
+            const uint32_t t = s_warp[w];
+            run += (uint32_t) w < warp ? t : 0u;
+            total += t;
+        }
+        run += total << 16; // the upper-half threads' keys come after all lower-half ones
+        #pragma unroll
+        for (uint32_t j = 0; j < G; ++j) {
+            uint4 v = seg[(j + rot) % G], o;
+            o.x = run; run += v.x;
+            o.y = run; run += v.y;
+            o.z = run; run += v.z;
+            o.w = run; run += v.w;
+            seg[(j + rot) % G] = o;
+        }
+    }
+    __syncthreads();
+
+    // ---- where every run is staged and where it goes.  Run r < bins: digit r of the
+    // lower-half threads; run bins + d: digit d of the upper-half threads.
+    if (tid < 2 * bins) {
+        auto run_start = [&](uint32_t r) -> uint32_t { // sorted-tile slot of the run's first key
+            if (r >= 2 * bins)
+                return tile_count;
+            const uint32_t d = r < bins ? r : r - bins;
+            return ((const uint16_t *) s_cnt)[d * (HALF * 2) + (r < bins ? 0 : 1)];
+        };
+        const uint32_t ls = run_start(tid), le = run_start(tid + 1);
+        uint32_t gpos = gstart;
+        if (tid >= bins) // after the lower-half threads' keys of the same digit
+            gpos += run_start(tid - bins + 1) - run_start(tid - bins);
+        const uint32_t galign = (uint32_t) (((uintptr_t) (out0 + gpos)) >> 2) & 3u;
+        const uint32_t pos = ((ls + RK_PAD * tid + 3u) & ~3u) + galign;
+        s_shift[tid] = pos - ls;
+        s_pos[tid] = pos;
+        s_len[tid] = le - ls;
+        s_gpos[tid] = gpos;
+    }
+    uint32_t idx[IN == RK_PAIRS ? RK_ITEMS : 1];
+    if constexpr (IN == RK_PAIRS)
+        load16(in1, idx);
+    __syncthreads();
+
+    // ---- sort into the staging area (values are final: what is stored to global)
+    uint32_t slot2[OUT == RK_OUT_PAIRS ? RK_ITEMS / 2 : 1] = {};
+    const uint32_t idxmask = ib >= 32 ? 0xffffffffu : (1u << ib) - 1u;
+    const uint32_t *shift_mine = s_shift + (tid / HALF) * bins;
+    #pragma unroll
+    for (int i = 0; i < RK_ITEMS; ++i) {
+        if (FULL || first + i < tile_count) {
+            const uint32_t d = digit(key[i]);
+            const uint32_t sl = *(const uint16_t *) (cnt_mine + d * (HALF * 4)) +
+                                ((lr[i / 8] >> (4 * (i & 7))) & 15u) + shift_mine[d];
+            const uint32_t w = key[i];
+            uint32_t v;
+            if constexpr (IN == RK_RAW1) {
+                v = (uint32_t) base + first + i;
+            } else if constexpr (IN == RK_PACKED) {
+                v = OUT == RK_FINAL ? w & idxmask : ((w >> (ib + BITS)) << ib) | (w & idxmask);
+            } else {
+                const uint32_t ix = IN == RK_PAIRS ? idx[i] : (uint32_t) base + first + i;
+                if constexpr (OUT == RK_FINAL)
+                    v = ix;
+                else if constexpr (OUT == RK_OUT_PACKED)
+                    v = (((w & keymask) >> (shift + BITS)) << ib) | ix;
+                else
+                    v = w; // keys first, indices in a second round
+            }
+            s_stage[sl] = v;
+            if constexpr (OUT == RK_OUT_PAIRS)
+                slot2[i / 2] |= sl << (16 * (i & 1));
+        }
+    }
+
+    // a warp writes runs warp, warp + 16, ...
+    auto write_runs = [&](uint32_t *out) {
+        fence_proxy_async();
+        __syncthreads();
+        for (uint32_t r = warp; r < 2 * bins; r += RK_THREADS / 32) {
+            const uint32_t len = s_len[r];
+            if (len == 0)
+                continue;
+            const uint32_t *src = s_stage + s_pos[r];
+            uint32_t *dst = out + s_gpos[r];
+            if (len < 64) { // short run: one or two coalesced store instructions
+                for (uint32_t i = lane; i < len; i += 32)
+                    dst[i] = src[i];
+                continue;
+            }
+            const uint32_t head = (4u - (s_pos[r] & 3u)) & 3u;
+            const uint32_t mid = (len - head) & ~3u, tail = len - head - mid;
+            if (lane == 0) {
+                bulk_s2g(dst + head, src + head, mid * 4);
+                bulk_commit();
+            }
+            if (lane >= 1 && lane - 1 < head)
+                dst[lane - 1] = src[lane - 1];
+            else if (lane >= 4 && lane - 4 < tail)
+                dst[head + mid + lane - 4] = src[head + mid + lane - 4];
+        }
+    };
+    write_runs(out0);
+    if constexpr (OUT == RK_OUT_PAIRS) {
+        // second round: the indices travel through the same staging area
+        if (lane == 0)
+            bulk_wait_read<0>();
+        __syncthreads();
+        #pragma unroll
+        for (int i = 0; i < RK_ITEMS; ++i) {
+            if (FULL || first + i < tile_count)
+                s_stage[(slot2[i / 2] >> (16 * (i & 1))) & 0xffffu] =
+                    IN == RK_PAIRS ? idx[i] : (uint32_t) base + first + i;
+        }
+        write_runs(out1);
+    }
+    // the staging area must outlive the bulk copies that read it
+    if (lane == 0)
+        bulk_wait_read<0>();
+}
+
+template <int BITS, int IN, int OUT>
+__global__ void __launch_bounds__(RK_THREADS, RK_CTAS)
+mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
+                         const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
+                         uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
+                         uint32_t ahead_tiles, uint32_t *__restrict__ out0, uint32_t *__restrict__ out1) {
+    constexpr bool TWO = IN == RK_RAW || IN == RK_PAIRS;
+    static_assert(BITS >= 3 && BITS <= 6, "3..6-bit digits");
+    static_assert(TWO ? OUT != RK_FINAL || IN == RK_PAIRS : OUT != RK_OUT_PAIRS, "unsupported combination");
+    extern __shared__ __align__(16) uint32_t rk_smem[];
+    if ((uint64_t) (blockIdx.x + 1) * RK_TILE <= size)
+        rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, out0, out1, rk_smem);
+    else
+        rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, out0, out1, rk_smem);
+}
+
+struct RkArgs {
+    const uint32_t *in0, *in1, *table;
+    uint64_t size;
+    uint32_t ntiles, shift, mask, bins, ib, keymask;
+    uint32_t *out0, *out1;
+};
+
+template <int BITS, int IN, int OUT>
+static cudaError_t rk_launch_one(cudaStream_t stream, const RkArgs &a) {
+    constexpr size_t smem = rk_smem_bytes<BITS>();
+    auto kernel = mkperm_rank_place_kernel<BITS, IN, OUT>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess)
+        return err;
+    kernel<<<a.ntiles, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.size, a.ntiles, a.shift, a.mask,
+                                                   a.bins, a.ib, a.keymask, (uint32_t) (RK_CTAS * sm_count()),
+                                                   a.out0, a.out1);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int BITS>
+static cudaError_t rk_launch_bits(cudaStream_t stream, int in, int out, const RkArgs &a) {
+    switch (in * 4 + out) {
+        case RK_RAW1 * 4 + RK_FINAL: return rk_launch_one<BITS, RK_RAW1, RK_FINAL>(stream, a);
+        case RK_RAW * 4 + RK_OUT_PAIRS: return rk_launch_one<BITS, RK_RAW, RK_OUT_PAIRS>(stream, a);
+        case RK_RAW * 4 + RK_OUT_PACKED: return rk_launch_one<BITS, RK_RAW, RK_OUT_PACKED>(stream, a);
+        case RK_PAIRS * 4 + RK_FINAL: return rk_launch_one<BITS, RK_PAIRS, RK_FINAL>(stream, a);
+        case RK_PAIRS * 4 + RK_OUT_PAIRS: return rk_launch_one<BITS, RK_PAIRS, RK_OUT_PAIRS>(stream, a);
+        case RK_PAIRS * 4 + RK_OUT_PACKED: return rk_launch_one<BITS, RK_PAIRS, RK_OUT_PACKED>(stream, a);
+        case RK_PACKED * 4 + RK_FINAL: return rk_launch_one<BITS, RK_PACKED, RK_FINAL>(stream, a);
+        case RK_PACKED * 4 + RK_OUT_PACKED: return rk_launch_one<BITS, RK_PACKED, RK_OUT_PACKED>(stream, a);
+    }
+    return cudaErrorInvalidValue;
+}
+
+static cudaError_t rk_launch(cudaStream_t stream, int bits, int in, int out, const RkArgs &a) {
+    switch (bits) {
+        case 3: return rk_launch_bits<3>(stream, in, out, a);
+        case 4: return rk_launch_bits<4>(stream, in, out, a);
+        case 5: return rk_launch_bits<5>(stream, in, out, a);
+        case 6: return rk_launch_bits<6>(stream, in, out, a);
+    }
+    return cudaErrorInvalidValue;
 }
 
 static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t size,
                             uint32_t bins, uint32_t *hist) {
     B200_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t) bins * sizeof(uint32_t), stream));
     const int sms = sm_count();
-    size_t smem = (size_t) bins * sizeof(uint32_t);
-    if (smem <= 200 * 1024) {
+    constexpr uint32_t SWEEP_BINS = 49152; // 192 KiB of counters per CTA
+    if (bins <= 8 * SWEEP_BINS) {
+        // keys beyond one table: one sweep over the array per sub-range of the keys
+        const uint32_t sweeps = (uint32_t) ceil_div(bins, SWEEP_BINS);
+        const uint32_t per = (uint32_t) ceil_div(bins, sweeps);
+        const size_t smem = (size_t) per * sizeof(uint32_t);
         if (smem > 48 * 1024)
             B200_CUDA_CHECK(cudaFuncSetAttribute(histogram_smem_kernel,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -507,13 +722,174 @@ static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t 
         uint32_t per_sm = smem <= 32 * 1024 ? 2 : 1;
         uint32_t grid = (uint32_t) std::max<uint64_t>(
             1, std::min<uint64_t>((uint64_t) sms * per_sm, ceil_div(size, 4096)));
-        histogram_smem_kernel<<<grid, 1024, smem, stream>>>(keys, size, bins, hist);
+        for (uint32_t lo = 0; lo < bins; lo += per) {
+            histogram_smem_kernel<<<grid, 1024, smem, stream>>>(keys, size, lo, std::min(per, bins - lo),
+                                                                bins, hist);
+            count_launch();
+        }
     } else {
         uint32_t grid = (uint32_t) std::max<uint64_t>(
             1, std::min<uint64_t>((uint64_t) sms * 8, ceil_div(size, 256)));
         histogram_global_kernel<<<grid, 256, 0, stream>>>(keys, size, bins, hist);
+        count_launch();
     }
-    B200_LAUNCH_CHECK();
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return cuda_fail(err, "kernel launch");
+    return B200_OK;
+}
+
+/// Bucket-count histogram: one shared-memory table per CTA when it fits, a few
+/// sweeps over key sub-ranges when it does not (global atomics only beyond that).
+static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t size,
+                            uint32_t bins, uint32_t *hist);
+
+/// block_size == size: ranked tile passes (see mkperm_rank_place_kernel)
+static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint32_t size,
+                               uint32_t bucket_count, uint32_t *perm, uint32_t *offsets) {
+    uint32_t total_bits = 1;
+    while (total_bits < 32 && (1ull << total_bits) < bucket_count)
+        total_bits++;
+    uint32_t ib = 1;
+    while (ib < 32 && (1ull << ib) < size)
+        ib++;
+    const uint32_t npasses = (total_bits + 5) / 6;
+    const uint32_t ntiles = (uint32_t) ceil_div(size, RK_TILE);
+    const uint32_t keymask = total_bits >= 32 ? 0xffffffffu : (1u << total_bits) - 1u;
+
+    // digit widths: as even as possible, wider digits last (a wide digit costs
+    // counters and runs; the last passes move one word per element, not two)
+    uint32_t width[8], shift_of[8];
+    for (uint32_t p = 0, sh = 0; p < npasses; ++p) {
+        width[p] = total_bits / npasses + (p >= npasses - total_bits % npasses ? 1 : 0);
+        shift_of[p] = sh;
+        sh += width[p];
+    }
+
+    const uint64_t max_counts = (uint64_t) 64 * ntiles;
+    uint32_t *table = (uint32_t *) temp_alloc(max_counts * 4, stream);
+    uint32_t *tmp[4] = { nullptr, nullptr, nullptr, nullptr };
+    auto cleanup = [&]() {
+        temp_free(table, stream);
+        for (auto t : tmp)
+            temp_free(t, stream);
+    };
+    if (!table)
+        return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
+
+    int form = npasses == 1 ? RK_RAW1 : RK_RAW; // how elements reach the current pass
+    const uint32_t *in0 = values, *in1 = nullptr;
+    for (uint32_t p = 0; p < npasses; ++p) {
+        const bool last = p + 1 == npasses;
+        const uint32_t consumed = shift_of[p] + width[p];
+        RkArgs a{};
+        a.in0 = in0;
+        a.in1 = in1;
+        a.table = table;
+        a.size = size;
+        a.ntiles = ntiles;
+        a.ib = ib;
+        a.keymask = keymask;
+        if (form == RK_RAW1) {
+            a.shift = 0;
+            a.mask = 0xffffffffu;
+            a.bins = bucket_count;
+        } else {
+            a.shift = form == RK_PACKED ? ib : shift_of[p];
+            a.mask = (1u << width[p]) - 1u;
+            a.bins = last ? ((bucket_count - 1) >> shift_of[p]) + 1 : 1u << width[p];
+            a.bins = std::min(a.bins, 1u << width[p]);
+        }
+        int out;
+        if (last)
+            out = RK_FINAL;
+        else
+            out = (total_bits - consumed) + ib <= 32 ? RK_OUT_PACKED : RK_OUT_PAIRS;
+        if (last) {
+            a.out0 = perm;
+        } else {
+            const int set = (p & 1) * 2;
+            for (int i = set; i < set + (out == RK_OUT_PAIRS ? 2 : 1); ++i) {
+                if (!tmp[i])
+                    tmp[i] = (uint32_t *) temp_alloc((size_t) size * 4, stream);
+                if (!tmp[i]) {
+                    cleanup();
+                    return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
+                }
+            }
+            a.out0 = tmp[set];
+            a.out1 = tmp[set + 1];
+        }
+
+        const uint64_t ncounts = (uint64_t) a.bins * ntiles;
+        mkperm_tile_hist_kernel<<<(uint32_t) ceil_div(ntiles, MT_GROUP), MT_THREADS,
+                                  (size_t) MT_GROUP * a.bins * 4, stream>>>(
+            in0, size, ntiles, a.shift, a.mask, a.bins, table);
+        count_launch();
+        int rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts, ncounts, 1, 0,
+                                          table, table);
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+        // single pass: bucket starts are a strided view of the scanned table
+        if (npasses == 1 && offsets) {
+            uint32_t *records = (uint32_t *) temp_alloc(((size_t) bucket_count * 4 + 1) * 4, stream);
+            if (!records) {
+                cleanup();
+                return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
+            }
+            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(table, ntiles, bucket_count, size, records);
+            count_launch();
+            cudaError_t err = cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
+                                              cudaMemcpyDeviceToHost, stream);
+            temp_free(records, stream);
+            if (err != cudaSuccess) {
+                cleanup();
+                return cuda_fail(err, "cudaMemcpyAsync(offsets)");
+            }
+        }
+        const uint32_t bits = form == RK_RAW1 ? std::max(3u, total_bits) : std::max(3u, width[p]);
+        cudaError_t err = rk_launch(stream, (int) bits, form, out, a);
+        if (err != cudaSuccess) {
+            cleanup();
+            return cuda_fail(err, "mkperm_rank_place_kernel");
+        }
+        in0 = a.out0;
+        in1 = out == RK_OUT_PAIRS ? a.out1 : nullptr;
+        form = out == RK_OUT_PAIRS ? RK_PAIRS : RK_PACKED;
+    }
+
+    // several passes: bucket sizes come from a whole-array histogram of the full key
+    if (npasses > 1 && offsets) {
+        size_t hist_words = ((size_t) bucket_count + 3) & ~(size_t) 3; // keep records 16-byte aligned
+        uint32_t *hist = (uint32_t *) temp_alloc((hist_words + (size_t) bucket_count * 4 + 1) * 4, stream);
+        if (!hist) {
+            cleanup();
+            return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
+        }
+        uint32_t *records = hist + hist_words;
+        int rc = histogram_launch(stream, values, size, bucket_count, hist);
+        if (!rc)
+            rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, bucket_count,
+                                          bucket_count, 1, 0, hist, hist);
+        if (!rc) {
+            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(hist, 1, bucket_count, size, records);
+            count_launch();
+            rc = cuda_fail(cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
+                                           cudaMemcpyDeviceToHost, stream),
+                           "cudaMemcpyAsync(offsets)");
+        }
+        temp_free(hist, stream);
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+    }
+    cleanup();
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return cuda_fail(err, "kernel launch");
     return B200_OK;
 }
 
@@ -560,18 +936,29 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     const int sms = sm_count();
     const uint64_t ngroups = ceil_div(size, block_size);
 
+    if (ngroups == 1) {
+        rc = mkperm_single_group(stream, values, size, bucket_count, perm, offsets);
+        if (rc)
+            return rc;
+        if (offsets) {
+            // the reference waits on an event here (src/cuda_ts.cpp:964-967)
+            B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (unique)
+                *unique = offsets[4 * (size_t) bucket_count];
+        }
+        return B200_OK;
+    }
+
     // ---- digit plan
     uint32_t total_bits = 0;
     while (total_bits < 32 && (1ull << total_bits) < bucket_count)
         total_bits++;
-    const bool tiled = ngroups == 1; // one sorting group: tile kernels
-    const uint32_t digit_bits = tiled ? 10 : 11;
+    const uint32_t digit_bits = 11;
     uint32_t npasses = 1, bits_per = 0;
-    if (bucket_count > (tiled ? MT_MAX_BINS : MKPERM_MAX_BINS)) {
+    if (bucket_count > MKPERM_MAX_BINS) {
         npasses = (total_bits + digit_bits - 1) / digit_bits;
         bits_per = (total_bits + npasses - 1) / npasses;
     }
-    const uint32_t ntiles = (uint32_t) ceil_div(size, MT_TILE);
 
     // ---- row geometry (shared by all passes)
     uint32_t max_bins = npasses == 1 ? bucket_count : (1u << bits_per);
@@ -584,14 +971,7 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     }
 
     size_t smem = (size_t) MKPERM_WARPS * max_bins * sizeof(uint32_t);
-    if (tiled) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_place_kernel<false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int) tile_place_smem(MT_MAX_BINS)));
-        B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_place_kernel<true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int) tile_place_smem(MT_MAX_BINS)));
-    } else if (smem > 48 * 1024) {
+    if (smem > 48 * 1024) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_hist_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         B200_CUDA_CHECK(cudaFuncSetAttribute(mkperm_place_kernel,
@@ -599,7 +979,7 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     }
 
     // groups per launch so that the count table stays below 1 GiB
-    uint64_t counts_per_group = (uint64_t) max_bins * (tiled ? ntiles : rows_per_group);
+    uint64_t counts_per_group = (uint64_t) max_bins * rows_per_group;
     uint64_t groups_per_launch = std::max<uint64_t>(1, (1ull << 28) / counts_per_group);
     groups_per_launch = std::min(groups_per_launch, ngroups);
     if (counts_per_group >= (1ull << 31))
@@ -646,45 +1026,6 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
         uint32_t *keys_out = last ? nullptr : tmp[(pass & 1) * 2];
         uint32_t *idx_out = last ? perm : tmp[(pass & 1) * 2 + 1];
         size_t pass_smem = (size_t) MKPERM_WARPS * g.bins * sizeof(uint32_t);
-
-        if (tiled) {
-            const uint64_t ncounts = (uint64_t) g.bins * ntiles;
-            mkperm_tile_hist_kernel<<<(uint32_t) ceil_div(ntiles, MT_GROUP), MT_THREADS,
-                                      (size_t) MT_GROUP * g.bins * 4, stream>>>(
-                keys_in, size, ntiles, g.shift, g.mask, g.bins, counts);
-            count_launch();
-            rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts, ncounts, 1, 0,
-                                          counts, counts);
-            if (rc) {
-                cleanup();
-                return rc;
-            }
-            // single pass: bucket starts are a strided view of the scanned table
-            if (last && npasses == 1 && offsets) {
-                uint32_t *records = (uint32_t *) temp_alloc(((size_t) bucket_count * 4 + 1) * 4, stream);
-                if (!records) {
-                    cleanup();
-                    return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
-                }
-                mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(counts, ntiles, bucket_count, size, records);
-                count_launch();
-                cudaError_t err = cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
-                                                  cudaMemcpyDeviceToHost, stream);
-                temp_free(records, stream);
-                if (err != cudaSuccess) {
-                    cleanup();
-                    return cuda_fail(err, "cudaMemcpyAsync(offsets)");
-                }
-            }
-            if (idx_in)
-                mkperm_tile_place_kernel<true><<<ntiles, MT_THREADS, tile_place_smem(g.bins), stream>>>(
-                    keys_in, idx_in, counts, size, ntiles, g.shift, g.mask, g.bins, idx_out, keys_out);
-            else
-                mkperm_tile_place_kernel<false><<<ntiles, MT_THREADS, tile_place_smem(g.bins), stream>>>(
-                    keys_in, idx_in, counts, size, ntiles, g.shift, g.mask, g.bins, idx_out, keys_out);
-            count_launch();
-            continue;
-        }
 
         for (uint64_t g0 = 0; g0 < ngroups; g0 += groups_per_launch) {
             g.group0 = g0;

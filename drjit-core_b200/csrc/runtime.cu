@@ -153,6 +153,23 @@ void temp_free(void *ptr, cudaStream_t stream) {
         cudaFreeAsync(ptr, stream);
 }
 
+// One pinned host word per calling thread.  Kernels of the synchronising entry
+// points (jit_compress) write their scalar result straight into it (pinned memory
+// is device-accessible under unified addressing), so the host reads it after the
+// stream synchronisation without a device-to-host copy into pageable memory.  The
+// reference reads its count from pinned memory in the same way
+// (src/cuda_ts.cpp:759-762).
+uint32_t *pinned_scalar() {
+    static thread_local uint32_t *word = nullptr;
+    if (!word) {
+        if (cudaHostAlloc((void **) &word, 64, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            word = nullptr;
+        }
+    }
+    return word;
+}
+
 // Typed fill: 'count' elements of 2 / 4 / 8 bytes.  16-byte stores in the body,
 // element stores for the unaligned head and the tail.
 template <typename T>

@@ -9,11 +9,20 @@
 //
 // Modes (jit.h:1017-1066):
 //   Direct       one red.global per element;
-//   Local        lanes that hit the same address are found with match.any and
-//                merged (butterfly when all 32 agree, else a rank-halving
-//                tree); the lowest lane issues the single atomic;
-//   Auto         Local (as in the reference's default flag set), except that a
-//                warp whose probe batches show no conflicts issues directly;
+//   Local        lanes that hit the same address are merged before the atomic.
+//                The reference finds them with match.any, which on B200 costs
+//                256 issue cycles per warp instruction whenever the lanes disagree
+//                (tools/ubench_warp_ops.cu) -- more than the 32 atomics it can
+//                save.  Here a warp picks one of two mergers per batch group from
+//                a periodic probe:
+//                  runs   neighbouring lanes with equal addresses (what coherent
+//                         scatters produce) are merged by a segmented shuffle
+//                         reduction -- one shuffle-up, one compare, one ballot to
+//                         find the runs; a butterfly when the whole warp agrees;
+//                  match  match.any + rank-halving tree, kept for the case where
+//                         many duplicates are NOT adjacent (few distinct targets);
+//   Auto         Local, except that a warp whose probe shows (almost) no
+//                duplicates issues its atomics directly;
 //   NoConflicts  plain load / op / store.
 #include "common.cuh"
 
@@ -162,12 +171,50 @@ B200_DEVICE uint32_t scatter_local(T *target, uint32_t idx, T v, bool on, uint32
     return absorbed;
 }
 
-/// MODE: Direct / Local / NoConflicts as in jit.h:1017-1066.  ADAPTIVE (Auto):
-/// Local, except that a warp which finds (almost) no address conflicts in a
-/// probe batch issues the next batches directly -- finding the peers
-/// (match.any over 32 distinct addresses) costs more than the atomics it saves
-/// when indices are incoherent.  Every eighth batch is a probe.
-template <typename T, int Op, int MODE, bool ADAPTIVE, int U>
+/// Warp pre-reduction of RUNS of neighbouring lanes with equal addresses; the
+/// first lane of every run issues the atomic.  Duplicates that are not adjacent
+/// stay separate atomics (still correct).
+template <typename T, int Op>
+B200_DEVICE void scatter_runs(T *target, uint32_t idx, T v, bool on, uint32_t lane) {
+    const uint32_t prev_idx = __shfl_up_sync(FULL_MASK, idx, 1);
+    const uint32_t active = __ballot_sync(FULL_MASK, on);
+    // a lane starts a run unless its lower neighbour is active with the same index
+    const bool head = lane == 0 || idx != prev_idx || !((active >> (lane - 1)) & 1u) || !on;
+    const uint32_t heads = __ballot_sync(FULL_MASK, head);
+    if (heads == 1u) {
+        // the whole warp hits one address
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+            v = ElemOp<T, Op>::apply(v, shfl_elem<T>(FULL_MASK, v, lane ^ d));
+        if (lane == 0)
+            Atomic<T, Op>::apply(target + idx, v);
+        return;
+    }
+    if (heads != FULL_MASK) {
+        // last lane of this lane's run: one below the next head (inactive lanes are
+        // heads of their own, so a run never extends over them)
+        const uint32_t above = heads & ~((2u << lane) - 1u);
+        const uint32_t last = above ? (uint32_t) __ffs(above) - 2u : 31u;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T other = shfl_elem<T>(FULL_MASK, v, min(lane + d, 31u));
+            if (lane + d <= last)
+                v = ElemOp<T, Op>::apply(v, other);
+        }
+    }
+    if (head && on)
+        Atomic<T, Op>::apply(target + idx, v);
+}
+
+/// MODE: Direct / Local / NoConflicts as in jit.h:1017-1066.  Local picks its
+/// merger per warp from a probe (every eighth batch, first step): match.any counts
+/// all duplicates among the 32 addresses, the run detection the adjacent ones.
+///   AUTO and (almost) no duplicates          -> direct atomics
+///   most duplicates adjacent (or none)       -> scatter_runs
+///   otherwise                                -> scatter_local (match.any)
+enum { PATH_DIRECT = 0, PATH_RUNS = 1, PATH_MATCH = 2 };
+
+template <typename T, int Op, int MODE, bool AUTO, int U>
 __global__ void __launch_bounds__(SCATTER_THREADS)
 scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                       const uint32_t *__restrict__ index, const uint8_t *__restrict__ mask,
@@ -175,7 +222,7 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
     const uint64_t first = (uint64_t) blockIdx.x * SCATTER_THREADS + threadIdx.x;
-    bool local = true;   // warp-uniform
+    int path = PATH_RUNS; // warp-uniform
     uint32_t batch = 0;
 
     // all lanes of a warp run the same number of iterations (warp collectives)
@@ -187,6 +234,7 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
         for (int u = 0; u < U; ++u) {
             uint64_t i = base + lane + (uint64_t) u * stride;
             on[u] = i < n;
+            idx[u] = 0;
             if (on[u]) {
                 idx[u] = __ldcs(index + i);
                 val[u] = __ldcs(value + i);
@@ -194,7 +242,7 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                     on[u] = __ldcs(mask + i) != 0;
             }
         }
-        const bool probe = ADAPTIVE && (batch & 7) == 0;
+        const bool probe = MODE == B200_MODE_LOCAL && (batch & 7) == 0;
         #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (base + (uint64_t) u * stride >= n)
@@ -208,10 +256,25 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                 if (on[u])
                     Atomic<T, Op>::apply(target + idx[u], val[u]);
             } else {
-                if (!ADAPTIVE || local || (probe && u == 0)) {
-                    const uint32_t absorbed = scatter_local<T, Op>(target, idx[u], val[u], on[u], lane);
-                    if (probe && u == 0)
-                        local = __shfl_sync(FULL_MASK, absorbed, __ffs(__ballot_sync(FULL_MASK, on[u]) | 0x80000000u) - 1) >= 4;
+                if (probe && u == 0) {
+                    // adjacent duplicates (what scatter_runs would merge)
+                    const uint32_t prev_idx = __shfl_up_sync(FULL_MASK, idx[u], 1);
+                    const uint32_t active = __ballot_sync(FULL_MASK, on[u]);
+                    const bool cont = lane != 0 && on[u] && idx[u] == prev_idx && ((active >> (lane - 1)) & 1u);
+                    const uint32_t adjacent = __popc(__ballot_sync(FULL_MASK, cont));
+                    // all duplicates (and the merged atomics of this step)
+                    const uint32_t all = scatter_local<T, Op>(target, idx[u], val[u], on[u], lane);
+                    const uint32_t dup = __shfl_sync(FULL_MASK, all, __ffs(active | 0x80000000u) - 1);
+                    if (AUTO && dup < 4)
+                        path = PATH_DIRECT;
+                    else if (4 * (dup - adjacent) <= dup)
+                        path = PATH_RUNS;
+                    else
+                        path = PATH_MATCH;
+                } else if (path == PATH_RUNS) {
+                    scatter_runs<T, Op>(target, idx[u], val[u], on[u], lane);
+                } else if (path == PATH_MATCH) {
+                    scatter_local<T, Op>(target, idx[u], val[u], on[u], lane);
                 } else if (on[u]) {
                     Atomic<T, Op>::apply(target + idx[u], val[u]);
                 }

@@ -70,6 +70,27 @@ def test_compress_misaligned_and_edges(dr, O):
     assert not bad, bad
 
 
+def test_compress_misaligned_output_and_density_sweep(dr, O):
+    # the dense rows of the stream kernel leave through 16-byte aligned bulk copies
+    # with ragged ends: exercise every output alignment and densities on both sides
+    # of the sparse / dense row threshold
+    bad = []
+    for dens in (0.05, 0.09, 0.12, 0.3, 0.7, 1.0):
+        for off_in, off_out in ((0, 0), (0, 1), (3, 2), (7, 3)):
+            size = 700001 + 4097 * off_out
+            m = mask_input(size, dens, salt=off_out)
+            d_in = to_dev(m, off_in)
+            d_out = empty_dev(size + 8, np.uint32, off_out)
+            d_out.fill_(-1)
+            cnt = dr.jit_compress(CUDA, d_in, size, d_out)
+            got = to_host(d_out, np.uint32)
+            ridx, rcnt = O.compress(m)
+            if cnt != rcnt or not np.array_equal(got[:cnt], ridx) or \
+               not np.all(got[cnt:cnt + 8] == 0xffffffff):
+                bad.append((dens, off_in, off_out, cnt, rcnt))
+    assert not bad, bad
+
+
 def test_compress_full_size(dr, O):
     # BASELINE.json configs[2]: 2^28-element mask at densities 0.01 / 0.5 / 0.99
     n = 1 << 28
@@ -156,8 +177,27 @@ def test_mkperm_skewed_and_no_offsets(dr, O):
         assert uq0 == 0 and np.array_equal(perm, rperm)
 
 
+def test_mkperm_wide_keys_all_pass_forms(dr):
+    # many digit passes: elements travel as (key, index) pairs first and as one
+    # packed word once the remaining key bits fit beside the index; the stable
+    # permutation is numpy's stable argsort.  Offsets are not requested (4 * B + 1
+    # words would not fit for these bucket counts).
+    rng = np.random.default_rng(7)
+    for size, buckets in ((100000, 1 << 30), (100001, (1 << 24) + 1), (1 << 20, 1 << 18),
+                          (8191, 0xffffffff), (300000, 70), (300000, 1 << 12), (300000, (1 << 13) + 5)):
+        k = rng.integers(0, buckets, size, dtype=np.uint64).astype(np.uint32)
+        k[:7] = buckets - 1
+        for off in (0, 1):
+            d_k = to_dev(k, off)
+            d_perm = empty_dev(size, np.uint32, off)
+            uq = dr.jit_block_mkperm(CUDA, d_k, size, size, buckets, d_perm, None)
+            assert uq == 0
+            assert np.array_equal(to_host(d_perm, np.uint32),
+                                  np.argsort(k, kind="stable").astype(np.uint32)), (size, buckets, off)
+
+
 def test_mkperm_histogram(dr):
-    for size, buckets in ((1000, 7), (1 << 20, 1024), (1 << 20, 65536), (3000001, 100000)):
+    for size, buckets in ((1000, 7), (1 << 20, 1024), (1 << 20, 65536), (3000001, 100000), (1 << 20, 300000)):
         k = key_input(size, buckets)
         h = empty_dev(buckets, np.uint32)
         dr.mkperm_histogram(to_dev(k), size, buckets, h)

@@ -21,6 +21,8 @@ def index_input(n, m, kind):
         return ((i >> np.uint32(6)) % np.uint32(m)).astype(np.uint32)
     if kind == "same":
         return np.full(n, m // 2, dtype=np.uint32)
+    if kind == "runs":  # ragged runs of 1..7 equal indices that straddle warp boundaries
+        return ((np.cumsum(fmix32(i) % np.uint32(7) == 0) // 1) % m).astype(np.uint32)
     return ((i % np.uint32(3)) + (fmix32(i) % np.uint32(5) == 0) * (m - 3)).astype(np.uint32)  # few hot slots
 
 
@@ -42,7 +44,7 @@ def test_scatter_int(dr, O, tname):
         else:
             val = ((h.astype(np.uint64) << np.uint64(20)) ^ h.astype(np.uint64)).view(dt)
         mask = (fmix32(h) & np.uint32(3) != 0).astype(np.uint8)
-        for kind in ("random", "coherent", "same", "hot"):
+        for kind in ("random", "coherent", "same", "hot", "runs"):
             idx = index_input(n, m, kind)
             for opn in ("add", "min", "max", "and_", "or_"):
                 ident = O.reduce_identity(VT[tname], OP[opn])
@@ -71,7 +73,7 @@ def test_scatter_float(dr, O, tname, tol):
     for n, m in ((1000, 7), (1 << 20, 1 << 12), (100003, 997)):
         val = f32_input(n).astype(dt)
         sval = (val * 4 - 2).astype(dt)
-        for kind in ("random", "coherent", "hot"):
+        for kind in ("random", "coherent", "hot", "runs"):
             idx = index_input(n, m, kind)
             for mname, mode in MODES.items():
                 got = run_scatter(dr, VT[tname], OP["add"], np.zeros(m, dtype=dt), val, idx, None, mode)
