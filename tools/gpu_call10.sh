@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/cs_trace.py 0.01 > gpurun_out/cs_trace_001.txt 2>&1
-grep -A14 "resolve:" gpurun_out/cs_trace_001.txt
-tail -14 gpurun_out/cs_trace_001.txt
+timeout 600 python -m pytest tests/test_gpu_compress_mkperm.py -m gpu -x -q -k compress --timeout 600 -p no:cacheprovider > gpurun_out/test10.log 2>&1; echo "tests rc=$? $(tail -1 gpurun_out/test10.log)"
+timeout 300 python tools/perf_probe.py compress
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -c 60 --csv --log-file gpurun_out/launches10.csv python tools/ncu_targets.py compress > gpurun_out/ncu10.log 2>&1
