@@ -80,6 +80,8 @@ def lib():
         L.b200_block_mkperm.argtypes = [vp, vp, u32, u32, u32, vp, vp, ctypes.POINTER(u32)]
         L.b200_mkperm_histogram.argtypes = [vp, vp, u64, u32, vp]
         L.b200_scatter_reduce.argtypes = [vp, i, i, i, vp, vp, vp, vp, u64]
+        L.b200_scatter_inc.argtypes = [vp, vp, vp, vp, vp, u64]
+        L.b200_scatter_reduce_packet.argtypes = [vp, i, i, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
         L.b200_all_async.argtypes = [vp, vp, u64, vp]
         L.b200_any_async.argtypes = [vp, vp, u64, vp]
         L.b200_all.argtypes = [vp, vp, u64, ctypes.POINTER(i)]
@@ -270,6 +272,22 @@ def scatter_reduce(vt, op, target, value, index, mask, n, mode=ReduceMode.Auto,
     """target[index[i]] op= value[i] for i < n where mask[i] (mask may be None)."""
     _check(lib().b200_scatter_reduce(_stream(stream), vt, op, mode, _ptr(target),
                                      _ptr(value), _ptr(index), _ptr(mask), n))
+
+
+def scatter_inc(target, index, mask, out, n, stream=None):
+    """out[i] = target[index[i]]++ (atomically) for i < n where mask[i]; masked
+    entries receive 0 (jit_var_scatter_inc, jit.h:1125-1143)."""
+    _check(lib().b200_scatter_inc(_stream(stream), _ptr(target), _ptr(index), _ptr(mask),
+                                  _ptr(out), n))
+
+
+def scatter_reduce_packet(vt, op, target, values, index, mask, n, mode=ReduceMode.Auto,
+                          stream=None):
+    """target[index[i] * W + k] op= values[k][i] for the W = len(values) component
+    arrays (jit_var_scatter_packet with a reduction, jit.h:1117)."""
+    ptrs = (ctypes.c_void_p * len(values))(*[_ptr(v) for v in values])
+    _check(lib().b200_scatter_reduce_packet(_stream(stream), vt, op, mode, _ptr(target), ptrs,
+                                            len(values), _ptr(index), _ptr(mask), n))
 
 
 def jit_can_scatter_reduce(backend, vt, op):

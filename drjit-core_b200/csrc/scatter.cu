@@ -283,6 +283,244 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
     }
 }
 
+// ---------------------------------------------------------------- scatter_inc
+//
+// jit_var_scatter_inc (jit.h:1125-1143; emitter src/cuda_scatter.cpp:356-393):
+// atomically increment target[index[i]] and return the OLD value -- the building
+// block of queue-style stream compaction.  Warp aggregated like the reference (one
+// atomic per group of lanes with the same counter, every lane gets base + rank),
+// but the groups are found without match.any: a vote when the whole warp hits one
+// counter (the compaction case), runs of neighbouring equal indices otherwise.
+// Masked lanes receive 0 (src/cuda_scatter.cpp:361-364).
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_inc_kernel(uint32_t *__restrict__ target, const uint32_t *__restrict__ index,
+                   const uint8_t *__restrict__ mask, uint32_t *__restrict__ out, uint64_t n) {
+    constexpr int WARPS = SCATTER_THREADS / 32;
+    __shared__ uint32_t s_idx[WARPS], s_cnt[WARPS], s_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
+    // CTA-uniform trip count (the loop contains block-wide barriers)
+    for (uint64_t cbase = (uint64_t) blockIdx.x * SCATTER_THREADS; cbase < n; cbase += stride) {
+        const uint64_t i = cbase + threadIdx.x;
+        bool on = i < n;
+        uint32_t idx = 0;
+        if (on) {
+            idx = __ldcs(index + i);
+            if (mask)
+                on = __ldcs(mask + i) != 0;
+        }
+        const uint32_t active = __ballot_sync(FULL_MASK, on);
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t lead = __ffs(active | 0x80000000u) - 1;
+        const uint32_t lead_idx = __shfl_sync(FULL_MASK, idx, lead);
+        const bool warp_uniform = __all_sync(FULL_MASK, !on || idx == lead_idx);
+
+        // Whole CTA on one counter (queue compaction): ONE atomic per 256 entries --
+        // atomics on a single address are served one at a time by the L2 (measured:
+        // 2^21 warp-level atomics on one counter take 1.4 ms)
+        if (lane == 0) {
+            s_cnt[warp] = __popc(active);
+            s_idx[warp] = warp_uniform ? lead_idx : 0xffffffffu; // (index 2^32 - 1 takes the warp path)
+        }
+        __syncthreads();
+        uint32_t total = 0, before = 0, ref = 0xffffffffu;
+        bool cta_uniform = true;
+        #pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s_cnt[w], x = s_idx[w];
+            if (c) {
+                if (ref == 0xffffffffu)
+                    ref = x;
+                cta_uniform &= x == ref && x != 0xffffffffu;
+            }
+            total += c;
+            before += (uint32_t) w < warp ? c : 0u;
+        }
+        uint32_t old = 0;
+        if (cta_uniform && total) {
+            if (threadIdx.x == 0)
+                s_base = atomicAdd(target + ref, total);
+            __syncthreads();
+            old = s_base + before + __popc(active & lt);
+        } else if (active) {
+            if (warp_uniform) {
+                uint32_t prev = 0;
+                if (lane == lead)
+                    prev = atomicAdd(target + idx, (uint32_t) __popc(active));
+                prev = __shfl_sync(FULL_MASK, prev, lead);
+                old = prev + __popc(active & lt);
+            } else {
+                const uint32_t prev_idx = __shfl_up_sync(FULL_MASK, idx, 1);
+                const bool head = lane == 0 || idx != prev_idx || !((active >> (lane - 1)) & 1u) || !on;
+                const uint32_t heads = __ballot_sync(FULL_MASK, head);
+                // this lane's run: [my_head, last]
+                const uint32_t my_head = 31u - __clz(heads & (lt | (1u << lane)));
+                const uint32_t above = heads & ~((2u << lane) - 1u);
+                const uint32_t last = above ? (uint32_t) __ffs(above) - 2u : 31u;
+                uint32_t prev = 0;
+                if (head && on)
+                    prev = atomicAdd(target + idx, last - lane + 1u);
+                prev = __shfl_sync(FULL_MASK, prev, my_head);
+                old = prev + (lane - my_head);
+            }
+        }
+        if (i < n)
+            out[i] = on ? old : 0u;
+        __syncthreads(); // s_idx / s_cnt / s_base are rewritten in the next step
+    }
+}
+
+// -------------------------------------------------------------- packet scatter
+//
+// jit_var_scatter_packet with a reduction (jit.h:1117; emitter
+// jitc_cuda_render_scatter_reduce_packet, src/cuda_packet.cpp:169-327): every
+// element carries W (power of two) consecutive components,
+//   target[index[i] * W + k] op= values[k][i],   k < W,
+// i.e. an array-of-structures target (RGB(A) splats) fed from W separate arrays.
+// f32 Add uses the vector reductions of sm_90+ (red.global.add.v4.f32 / .v2.f32,
+// as the reference does for cc >= 90, cuda_packet.cpp:243-289): one L2 operation
+// per 16 bytes instead of four.  Everything else is W scalar atomics.  In Local /
+// Auto mode runs of neighbouring equal indices are merged first (component-wise
+// segmented shuffle reduction, as in scatter_runs).
+template <typename T, int W> struct PacketPtrs { const T *v[W]; };
+
+template <int W> B200_DEVICE void red_add_f32_vec(float *p, const float (&v)[W]) {
+    if constexpr (W % 4 == 0) {
+        #pragma unroll
+        for (int k = 0; k < W; k += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                         :: "l"(p + k), "f"(v[k]), "f"(v[k + 1]), "f"(v[k + 2]), "f"(v[k + 3]) : "memory");
+    } else if constexpr (W == 2) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+        atomicAdd(p, v[0]);
+    }
+}
+
+template <typename T, int Op, int W, bool MERGE>
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_packet_kernel(T *__restrict__ target, const PacketPtrs<T, W> values,
+                      const uint32_t *__restrict__ index, const uint8_t *__restrict__ mask,
+                      uint64_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
+    const uint64_t first = (uint64_t) blockIdx.x * SCATTER_THREADS + threadIdx.x;
+    for (uint64_t base = first - lane; base < n; base += stride) {
+        const uint64_t i = base + lane;
+        bool on = i < n;
+        uint32_t idx = 0;
+        T v[W];
+        if (on) {
+            idx = __ldcs(index + i);
+            #pragma unroll
+            for (int k = 0; k < W; ++k)
+                v[k] = __ldcs(values.v[k] + i);
+            if (mask)
+                on = __ldcs(mask + i) != 0;
+        }
+        bool issue = on;
+        if constexpr (MERGE) {
+            const uint32_t prev_idx = __shfl_up_sync(FULL_MASK, idx, 1);
+            const uint32_t active = __ballot_sync(FULL_MASK, on);
+            const bool head = lane == 0 || idx != prev_idx || !((active >> (lane - 1)) & 1u) || !on;
+            const uint32_t heads = __ballot_sync(FULL_MASK, head);
+            if (heads != FULL_MASK) {
+                const uint32_t above = heads & ~((2u << lane) - 1u);
+                const uint32_t last = above ? (uint32_t) __ffs(above) - 2u : 31u;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    #pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        const T other = shfl_elem<T>(FULL_MASK, v[k], min(lane + d, 31u));
+                        if (lane + d <= last)
+                            v[k] = ElemOp<T, Op>::apply(v[k], other);
+                    }
+                }
+            }
+            issue = head && on;
+        }
+        if (issue) {
+            T *p = target + (uint64_t) idx * W;
+            if constexpr (std::is_same<T, float>::value && Op == B200_OP_ADD && W >= 2) {
+                red_add_f32_vec<W>(p, v);
+            } else {
+                #pragma unroll
+                for (int k = 0; k < W; ++k)
+                    Atomic<T, Op>::apply(p + k, v[k]);
+            }
+        }
+    }
+}
+
+struct PacketCall {
+    cudaStream_t stream;
+    void *target;
+    const void *const *values;
+    uint32_t width;
+    const uint32_t *index;
+    const uint8_t *mask;
+    uint64_t n;
+    int mode;
+};
+
+template <typename T, int Op, int W> static int launch_packet_w(const PacketCall &c) {
+    PacketPtrs<T, W> ptrs;
+    for (int k = 0; k < W; ++k)
+        ptrs.v[k] = (const T *) c.values[k];
+    uint32_t grid = (uint32_t) std::max<uint64_t>(
+        1, std::min<uint64_t>(ceil_div(c.n, (uint64_t) SCATTER_THREADS), (uint64_t) sm_count() * 16));
+    if (c.mode == B200_MODE_DIRECT)
+        scatter_packet_kernel<T, Op, W, false><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+            (T *) c.target, ptrs, c.index, c.mask, c.n);
+    else
+        scatter_packet_kernel<T, Op, W, true><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+            (T *) c.target, ptrs, c.index, c.mask, c.n);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <typename T, int Op> static int launch_packet(const PacketCall &c) {
+    switch (c.width) {
+        case 1: return launch_packet_w<T, Op, 1>(c);
+        case 2: return launch_packet_w<T, Op, 2>(c);
+        case 4: return launch_packet_w<T, Op, 4>(c);
+        case 8: return launch_packet_w<T, Op, 8>(c);
+        default:
+            return fail(B200_ERR_UNSUPPORTED,
+                        "jit_var_scatter_packet(): packet size must be 1, 2, 4 or 8 (got %u)", c.width);
+    }
+}
+
+typedef int (*PacketFn)(const PacketCall &);
+
+static PacketFn pick_packet(int vt, int op) {
+    // the types / operations splatting uses; everything else: W calls of b200_scatter_reduce
+    if (vt == B200_VT_FLOAT32) {
+        switch (op) {
+            case B200_OP_ADD: return launch_packet<float, B200_OP_ADD>;
+            case B200_OP_MIN: return launch_packet<float, B200_OP_MIN>;
+            case B200_OP_MAX: return launch_packet<float, B200_OP_MAX>;
+        }
+    } else if (vt == B200_VT_UINT32) {
+        switch (op) {
+            case B200_OP_ADD: return launch_packet<uint32_t, B200_OP_ADD>;
+            case B200_OP_MIN: return launch_packet<uint32_t, B200_OP_MIN>;
+            case B200_OP_MAX: return launch_packet<uint32_t, B200_OP_MAX>;
+            case B200_OP_AND: return launch_packet<uint32_t, B200_OP_AND>;
+            case B200_OP_OR:  return launch_packet<uint32_t, B200_OP_OR>;
+        }
+    } else if (vt == B200_VT_INT32) {
+        switch (op) {
+            case B200_OP_ADD: return launch_packet<int32_t, B200_OP_ADD>;
+            case B200_OP_MIN: return launch_packet<int32_t, B200_OP_MIN>;
+            case B200_OP_MAX: return launch_packet<int32_t, B200_OP_MAX>;
+        }
+    } else if (vt == B200_VT_FLOAT64 && op == B200_OP_ADD) {
+        return launch_packet<double, B200_OP_ADD>;
+    }
+    return nullptr;
+}
+
 struct ScatterCall {
     cudaStream_t stream;
     void *target;
@@ -386,6 +624,49 @@ int b200_scatter_reduce(void *stream_, int vt, int op, int mode, void *target,
     if (n == 0)
         return B200_OK;
     ScatterCall call{ resolve_stream(stream_), target, value, index, mask, n, mode };
+    return fn(call);
+}
+
+int b200_scatter_inc(void *stream_, uint32_t *target, const uint32_t *index, const uint8_t *mask,
+                     uint32_t *out, uint64_t n) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    if (n == 0)
+        return B200_OK;
+    cudaStream_t stream = resolve_stream(stream_);
+    uint32_t grid = (uint32_t) std::max<uint64_t>(
+        1, std::min<uint64_t>(ceil_div(n, (uint64_t) SCATTER_THREADS), (uint64_t) sm_count() * 16));
+    scatter_inc_kernel<<<grid, SCATTER_THREADS, 0, stream>>>(target, index, mask, out, n);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int b200_scatter_reduce_packet(void *stream_, int vt, int op, int mode, void *target,
+                               const void *const *values, uint32_t width, const uint32_t *index,
+                               const uint8_t *mask, uint64_t n) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    if (width == 0 || (width & (width - 1)) != 0)
+        return fail(B200_ERR_INVALID, "jit_var_scatter_packet(): vector size must be a power of two!");
+    if (mode != B200_MODE_AUTO && mode != B200_MODE_DIRECT && mode != B200_MODE_LOCAL)
+        return fail(B200_ERR_UNSUPPORTED, "jit_var_scatter_packet(): unsupported reduction mode %d", mode);
+    PacketFn fn = pick_packet(vt, op);
+    if (!fn) {
+        // no packet kernel for this (type, op): component by component
+        if (!pick_scatter(vt, op))
+            return fail(B200_ERR_UNSUPPORTED,
+                        "jit_var_scatter_packet(): the %s backend does not support the requested type of "
+                        "atomic reduction (%s) for variables of type (%s)",
+                        "CUDA", op_name(op), type_name(vt));
+        return fail(B200_ERR_UNSUPPORTED,
+                    "jit_var_scatter_packet(): no packet kernel for (%s, %s); scatter the components "
+                    "one by one", type_name(vt), op_name(op));
+    }
+    if (n == 0)
+        return B200_OK;
+    PacketCall call{ resolve_stream(stream_), target, values, width, index, mask, n, mode };
     return fn(call);
 }
 

@@ -195,6 +195,26 @@ B200_API int b200_scatter_reduce(void *stream, int vt, int op, int mode, void *t
 /* jit_can_scatter_reduce (jit.h:1123) for the CUDA backend on sm_100 */
 B200_API int b200_can_scatter_reduce(int vt, int op);
 
+/* Stand-alone form of jit_var_scatter_inc (jit.h:1125-1143; emitter
+ * jitc_cuda_render_scatter_inc, src/cuda_scatter.cpp:356-393):
+ *   if (mask == NULL || mask[i]) { out[i] = target[index[i]]; target[index[i]] += 1; }
+ * atomically and warp aggregated; masked entries receive 0.  Which of several
+ * entries with the same index gets which old value is unspecified (as in the
+ * reference); the values handed out for a counter are consecutive. */
+B200_API int b200_scatter_inc(void *stream, uint32_t *target, const uint32_t *index,
+                              const uint8_t *mask, uint32_t *out, uint64_t n);
+
+/* Stand-alone form of the reducing packet scatter (jit_var_scatter_packet,
+ * jit.h:1117; emitter jitc_cuda_render_scatter_reduce_packet,
+ * src/cuda_packet.cpp:169-327):
+ *   if (mask == NULL || mask[i]) target[index[i] * width + k] op= values[k][i], k < width
+ * width in {1, 2, 4, 8}; values: HOST array of `width` device pointers (the
+ * reference takes `width` separate variables).  f32 / f64 Add, f32 Min / Max,
+ * u32 / i32 integer operations.  f32 Add issues red.global.add.v2/.v4.f32. */
+B200_API int b200_scatter_reduce_packet(void *stream, int vt, int op, int mode, void *target,
+                                        const void *const *values, uint32_t width,
+                                        const uint32_t *index, const uint8_t *mask, uint64_t n);
+
 /* --------------------------------------------------------------- telemetry */
 
 /* Number of kernels this library has launched since load (all threads). */

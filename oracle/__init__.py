@@ -107,6 +107,38 @@ class Oracle:
             raise ValueError(f"oracle_scatter_reduce: rc={rc}")
         return tgt
 
+    def scatter_reduce_packet(self, vt, op, target, values, index, mask=None, wide=False):
+        """src/cuda_packet.cpp:169-327 applied serially: target[index * W + k] op=
+        values[k] -- W independent scatters on the strided views of the target."""
+        width = len(values)
+        tgt = target.copy().reshape(-1, width)
+        for k in range(width):
+            col = self.scatter_reduce(vt, op, np.ascontiguousarray(tgt[:, k]), values[k], index, mask, wide)
+            tgt[:, k] = col
+        return tgt.reshape(-1)
+
+    @staticmethod
+    def scatter_inc_check(target_before, target_after, index, mask, out):
+        """Semantics of src/cuda_scatter.cpp:356-393 (the order in which entries of
+        one counter are served is unspecified): every counter grows by the number
+        of its active entries, those entries receive exactly the consecutive old
+        values base .. base + count - 1, masked entries receive 0.  Returns a list
+        of violations (empty = pass)."""
+        on = np.ones(index.shape[0], dtype=bool) if mask is None else mask.astype(bool)
+        bad = []
+        cnt = np.bincount(index[on], minlength=target_before.shape[0]).astype(np.uint32)
+        if not np.array_equal((target_before + cnt).astype(np.uint32), target_after):
+            bad.append("counters")
+        if np.any(out[~on] != 0):
+            bad.append("masked entries not zero")
+        order = np.lexsort((out[on], index[on]))
+        si, so = index[on][order], out[on][order].astype(np.int64)
+        start = np.r_[True, si[1:] != si[:-1]]
+        rank = np.arange(si.size) - np.maximum.accumulate(np.where(start, np.arange(si.size), 0))
+        if not np.array_equal(so, target_before[si].astype(np.int64) + rank):
+            bad.append("old values are not base + 0..count-1")
+        return bad
+
     def all(self, mask):
         return bool(self.lib.oracle_all(_ptr(mask), mask.shape[0]))
 

@@ -159,3 +159,69 @@ def test_scatter_full_size(dr, O):
     got = run_scatter(dr, VT["f32"], OP["add"], np.zeros(m, dtype=np.float32), fval, idx, None, 1)
     ref = O.scatter_reduce(VT["f32"], OP["add"], np.zeros(m, dtype=np.float32), fval, idx, wide=True)
     assert rel_err(got, ref) <= 1e-5
+
+
+def test_scatter_inc(dr, O):
+    # jit_var_scatter_inc (tests/mem.cpp:223-310 uses it for queue compaction):
+    # one shared counter, a few counters, runs, random; with and without a mask
+    bad = []
+    for n, m in ((1, 1), (1000, 1), (100003, 1), (100003, 7), (1 << 20, 1 << 10)):
+        h = u32_input(n)
+        mask = (fmix32(h) & np.uint32(3) != 0).astype(np.uint8)
+        for kind in ("same", "random", "coherent", "runs"):
+            idx = index_input(n, m, kind)
+            for mk in (None, mask):
+                before = (fmix32(np.arange(m, dtype=np.uint32)) & np.uint32(0xffff)).astype(np.uint32)
+                d_t = to_dev(before)
+                d_o = empty_dev(n, np.uint32)
+                d_o.fill_(-1)
+                dr.scatter_inc(d_t, to_dev(idx), None if mk is None else to_dev(mk), d_o, n)
+                viol = O.scatter_inc_check(before, to_host(d_t, np.uint32), idx, mk, to_host(d_o, np.uint32))
+                if viol:
+                    bad.append((n, m, kind, mk is not None, viol))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("width", [1, 2, 4, 8])
+def test_scatter_reduce_packet(dr, O, width):
+    # target[index * W + k] op= values[k]: integers bit-exact, f32 / f64 Add within the
+    # tolerance of the scalar scatter tests (the order of the atomics is unspecified)
+    bad = []
+    n, m = 100003, 997
+    for kind in ("random", "coherent", "runs", "same"):
+        idx = index_input(n, m, kind)
+        mask = (fmix32(u32_input(n)) & np.uint32(3) != 0).astype(np.uint8)
+        for mode in (1, 2, 0):
+            for mk in (None, mask):
+                ivals = [(u32_input(n) >> np.uint32(8 + k)).astype(np.uint32) for k in range(width)]
+                for opn in ("add", "min", "max", "and_", "or_"):
+                    ident = O.reduce_identity(VT["u32"], OP[opn]) & 0xFFFFFFFF
+                    tgt = np.full(m * width, ident, dtype=np.uint32)
+                    d_t = to_dev(tgt)
+                    dr.scatter_reduce_packet(VT["u32"], OP[opn], d_t, [to_dev(v) for v in ivals], to_dev(idx),
+                                             None if mk is None else to_dev(mk), n, mode=mode)
+                    ref = O.scatter_reduce_packet(VT["u32"], OP[opn], tgt, ivals, idx, mk)
+                    if not np.array_equal(to_host(d_t, np.uint32), ref):
+                        bad.append((kind, mode, mk is not None, opn))
+                fvals = [((u32_input(n) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24) + np.float32(k))
+                         for k in range(width)]
+                d_t = to_dev(np.zeros(m * width, dtype=np.float32))
+                dr.scatter_reduce_packet(VT["f32"], OP["add"], d_t, [to_dev(v) for v in fvals], to_dev(idx),
+                                         None if mk is None else to_dev(mk), n, mode=mode)
+                ref = O.scatter_reduce_packet(VT["f32"], OP["add"], np.zeros(m * width, dtype=np.float32),
+                                              fvals, idx, mk, wide=True)
+                got = to_host(d_t, np.float32)
+                if not np.allclose(got, ref, rtol=2e-5, atol=1e-30):  # fp32 Add: 2e-5 relative
+                    bad.append((kind, mode, mk is not None, "f32 add"))
+                for opn in ("min", "max"):
+                    tgt = np.full(m * width, np.inf if opn == "min" else -np.inf, dtype=np.float32)
+                    svals = [v - np.float32(0.5) for v in fvals]
+                    d_t = to_dev(tgt)
+                    dr.scatter_reduce_packet(VT["f32"], OP[opn], d_t, [to_dev(v) for v in svals], to_dev(idx),
+                                             None if mk is None else to_dev(mk), n, mode=mode)
+                    ref = O.scatter_reduce_packet(VT["f32"], OP[opn], tgt, svals, idx, mk)
+                    if not np.array_equal(to_host(d_t, np.float32), ref):
+                        bad.append((kind, mode, mk is not None, "f32 " + opn))
+    assert not bad, bad[:10]
+    with pytest.raises(RuntimeError):  # vector size must be a power of two
+        dr.scatter_reduce_packet(VT["f32"], OP["add"], 0, [0, 0, 0], 0, None, 1)

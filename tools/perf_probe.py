@@ -111,6 +111,31 @@ def main():
         ms = timeit(lambda: dr.scatter_reduce(F32, ADD, tgt, val, idx2, None, n2, mode=mode), iters=5)
         report(f"scatter_add f32 coherent {name}", ms, 8 * n2)
 
+    ms = timeit(lambda: dr.scatter_reduce(F32, ADD, tgt, val, idx2, None, n2, mode=0), iters=5)
+    report("scatter_add f32 coherent auto", ms, 8 * n2)
+    ms = timeit(lambda: dr.scatter_reduce(F32, ADD, tgt, val, idx, None, n2, mode=0), iters=5)
+    report("scatter_add f32 random auto", ms, 8 * n2)
+    # scatter_inc: one shared counter (queue compaction) and 2^20 random counters
+    cnt = torch.zeros(m2, device="cuda", dtype=torch.int32)
+    old = torch.empty(n2, device="cuda", dtype=torch.int32)
+    zero = torch.zeros(n2, device="cuda", dtype=torch.int32)
+    ms = timeit(lambda: dr.scatter_inc(cnt, zero, None, old, n2), iters=5)
+    report("scatter_inc one counter", ms, 8 * n2)
+    ms = timeit(lambda: dr.scatter_inc(cnt, idx, None, old, n2), iters=5)
+    report("scatter_inc random counters", ms, 8 * n2)
+    # packet scatter: 2^24 RGBA splats into 2^20 x 4 floats
+    n3 = 1 << 24
+    comps = [torch.rand(n3, device="cuda") for _ in range(4)]
+    tgt4 = torch.zeros(4 * m2, device="cuda")
+    for mode, name in ((1, "direct"), (0, "auto")):
+        ms = timeit(lambda: dr.scatter_reduce_packet(F32, ADD, tgt4, comps, idx, None, n3, mode=mode), iters=5)
+        report(f"scatter_add_packet f32x4 random {name} (2^24)", ms, 20 * n3)
+    def four_scalar():
+        for k in range(4):
+            dr.scatter_reduce(F32, ADD, tgt4, comps[k], idx, None, n3, mode=1)
+    ms = timeit(four_scalar, iters=5)
+    report("  same as 4 scalar scatters (layout differs)", ms, 32 * n3)
+
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "perf_probe.json"), "w") as f:
         json.dump(res, f, indent=1)
