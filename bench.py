@@ -610,6 +610,19 @@ def measure_primitives(torch, dr, dev, peak):
     keys.copy_((torch.arange(n2, dtype=torch.int64, device=dev) >> 6).to(torch.int32))
     ms = time_call(torch, lambda: dr.scatter_reduce(F32, ADD, tgt, val, keys, None, n2, mode=0))
     rec("scatter_add_f32_2^26_to_2^20_coherent_auto", ms, n2, 8 * n2)
+
+    # scatter_inc (jit_var_scatter_inc): one shared counter (queue compaction)
+    cnt = torch.zeros(m, dtype=torch.int32, device=dev)
+    keys.zero_()
+    ms = time_call(torch, lambda: dr.scatter_inc(cnt, keys, None, perm, n2))
+    rec("scatter_inc_2^26_one_counter", ms, n2, 8 * n2)
+    # reducing packet scatter: 2^24 four-component splats into 2^20 x 4 floats
+    n3 = 1 << 24
+    fill_input(torch, out_u32=keys, mod=m)
+    comps = [xf[k * n3:(k + 1) * n3] for k in range(4)]
+    tgt4 = torch.zeros(4 * m, dtype=torch.float32, device=dev)
+    ms = time_call(torch, lambda: dr.scatter_reduce_packet(F32, ADD, tgt4, comps, keys, None, n3, mode=0))
+    rec("scatter_add_packet_f32x4_2^24_to_2^20_random_auto", ms, n3, 20 * n3)
     return res
 
 
