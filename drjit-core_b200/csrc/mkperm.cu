@@ -400,7 +400,8 @@ template <int BITS> constexpr size_t rk_smem_bytes() {
 /// in0 / in1: keys (RAW*, PAIRS) or packed words (PACKED) / indices (PAIRS).
 /// digit = min((x >> shift) & mask, bins - 1) with x the key or the packed word.
 /// out0 / out1: permutation (FINAL), keys / indices (PAIRS), packed words (PACKED).
-/// ib: index bits of a packed word, keymask: the valid key bits.
+/// ib: index bits of a packed word, keymask: the valid key bits, index_base: index
+/// of element 0 (the permutation holds GLOBAL indices, resources/mkperm.cuh:373-376).
 ///
 /// Counters: the 16-bit counter of (digit d, thread t) lives in 32-bit word
 /// d * 256 + (t % 256), low half for t < 256, high half for t >= 256 -- so that the
@@ -418,8 +419,8 @@ template <int BITS, int IN, int OUT, bool FULL>
 B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
                          const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
                          uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
-                         uint32_t ahead_tiles, uint32_t *__restrict__ out0, uint32_t *__restrict__ out1,
-                         uint32_t *rk_smem) {
+                         uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
+                         uint32_t *__restrict__ out1, uint32_t *rk_smem) {
     constexpr uint32_t NB = 1u << BITS, WPT = NB / 2, G = WPT / 4, HALF = RK_THREADS / 2;
     constexpr uint32_t ROTM = G < HALF / 32 ? G : HALF / 32; // distinct rotations (see below)
     uint32_t *s_cnt = rk_smem;                              // NB * 256 packed counters
@@ -579,11 +580,11 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
             const uint32_t w = key[i];
             uint32_t v;
             if constexpr (IN == RK_RAW1) {
-                v = (uint32_t) base + first + i;
+                v = index_base + (uint32_t) base + first + i;
             } else if constexpr (IN == RK_PACKED) {
                 v = OUT == RK_FINAL ? w & idxmask : ((w >> (ib + BITS)) << ib) | (w & idxmask);
             } else {
-                const uint32_t ix = IN == RK_PAIRS ? idx[i] : (uint32_t) base + first + i;
+                const uint32_t ix = IN == RK_PAIRS ? idx[i] : index_base + (uint32_t) base + first + i;
                 if constexpr (OUT == RK_FINAL)
                     v = ix;
                 else if constexpr (OUT == RK_OUT_PACKED)
@@ -634,7 +635,7 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
         for (int i = 0; i < RK_ITEMS; ++i) {
             if (FULL || first + i < tile_count)
                 s_stage[(slot2[i / 2] >> (16 * (i & 1))) & 0xffffu] =
-                    IN == RK_PAIRS ? idx[i] : (uint32_t) base + first + i;
+                    IN == RK_PAIRS ? idx[i] : index_base + (uint32_t) base + first + i;
         }
         write_runs(out1);
     }
@@ -648,21 +649,22 @@ __global__ void __launch_bounds__(RK_THREADS, RK_CTAS)
 mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
                          const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
                          uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
-                         uint32_t ahead_tiles, uint32_t *__restrict__ out0, uint32_t *__restrict__ out1) {
+                         uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
+                         uint32_t *__restrict__ out1) {
     constexpr bool TWO = IN == RK_RAW || IN == RK_PAIRS;
     static_assert(BITS >= 3 && BITS <= 6, "3..6-bit digits");
     static_assert(TWO ? OUT != RK_FINAL || IN == RK_PAIRS : OUT != RK_OUT_PAIRS, "unsupported combination");
     extern __shared__ __align__(16) uint32_t rk_smem[];
     if ((uint64_t) (blockIdx.x + 1) * RK_TILE <= size)
-        rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, out0, out1, rk_smem);
+        rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem);
     else
-        rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, out0, out1, rk_smem);
+        rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem);
 }
 
 struct RkArgs {
     const uint32_t *in0, *in1, *table;
     uint64_t size;
-    uint32_t ntiles, shift, mask, bins, ib, keymask;
+    uint32_t ntiles, shift, mask, bins, ib, keymask, index_base;
     uint32_t *out0, *out1;
 };
 
@@ -675,7 +677,7 @@ static cudaError_t rk_launch_one(cudaStream_t stream, const RkArgs &a) {
         return err;
     kernel<<<a.ntiles, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.size, a.ntiles, a.shift, a.mask,
                                                    a.bins, a.ib, a.keymask, (uint32_t) (RK_CTAS * sm_count()),
-                                                   a.out0, a.out1);
+                                                   a.index_base, a.out0, a.out1);
     count_launch();
     return cudaGetLastError();
 }
@@ -746,12 +748,13 @@ static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t 
 
 /// block_size == size: ranked tile passes (see mkperm_rank_place_kernel)
 static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint32_t size,
-                               uint32_t bucket_count, uint32_t *perm, uint32_t *offsets) {
+                               uint32_t bucket_count, uint32_t *perm, uint32_t *offsets,
+                               uint32_t index_base = 0) {
     uint32_t total_bits = 1;
     while (total_bits < 32 && (1ull << total_bits) < bucket_count)
         total_bits++;
     uint32_t ib = 1;
-    while (ib < 32 && (1ull << ib) < size)
+    while (ib < 32 && (1ull << ib) < (uint64_t) index_base + size)
         ib++;
     const uint32_t npasses = (total_bits + 5) / 6;
     const uint32_t ntiles = (uint32_t) ceil_div(size, RK_TILE);
@@ -790,6 +793,7 @@ static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint
         a.ntiles = ntiles;
         a.ib = ib;
         a.keymask = keymask;
+        a.index_base = index_base;
         if (form == RK_RAW1) {
             a.shift = 0;
             a.mask = 0xffffffffu;
@@ -945,6 +949,20 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
             if (unique)
                 *unique = offsets[4 * (size_t) bucket_count];
+        }
+        return B200_OK;
+    }
+
+    // several LARGE sorting groups: one ranked-tile sort per group (the row kernels
+    // below rank with match.any, 256 issue cycles per warp instruction on B200)
+    if (ngroups <= 64 && block_size >= (1u << 17)) {
+        for (uint64_t g = 0; g < ngroups; ++g) {
+            const uint64_t start = g * block_size;
+            const uint32_t len = (uint32_t) std::min<uint64_t>(block_size, size - start);
+            rc = mkperm_single_group(stream, values + start, len, bucket_count, perm + start, nullptr,
+                                     (uint32_t) start);
+            if (rc)
+                return rc;
         }
         return B200_OK;
     }

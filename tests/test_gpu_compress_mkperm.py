@@ -154,7 +154,9 @@ def test_mkperm_blocked(dr, O):
     bad = []
     for size, bs, buckets in ((100000, 1000, 16), (100000, 12500, 300), (65536, 4096, 7),
                               (99999, 333, 40), (99999, 50000, 3000), (1000, 1, 5), (1000, 2, 5),
-                              (250000, 33333, 100000)):
+                              (250000, 33333, 100000),
+                              # large groups: one ranked-tile sort per group, global indices
+                              (1 << 20, 1 << 18, 16), (1500000, 400000, 1000), (3000001, 1 << 17, 70000)):
         k = key_input(size, buckets)
         perm, offs, uq = run_mkperm(dr, k, bs, buckets)
         rperm, _, ruq = O.block_mkperm(k, bs, buckets)
