@@ -223,51 +223,79 @@ histogram_global_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32
 
 /// Emit (id, start, size, 0) for every non-empty bucket in ascending id order.
 /// starts[b * stride] is the first output slot of bucket b; 'records' has room
-/// for 4 * bins + 1 words, the last one receiving the number of records.
+/// for 4 * bins + 1 words, the last one receiving the number of records.  One
+/// CTA: a warp owns ceil(bins / 1024) rows of 32 consecutive buckets (coalesced
+/// loads), counts its non-empty buckets, one block scan places the warps, a
+/// second walk writes the records.
 __global__ void __launch_bounds__(1024)
 mkperm_offsets_kernel(const uint32_t *__restrict__ starts, uint64_t stride, uint32_t bins,
                       uint32_t size, uint32_t *__restrict__ records) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t s_running;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0)
-        s_running = 0;
+    const uint32_t rows = (bins + 1023u) / 1024u;
+    const uint32_t warp_base = warp * rows * 32u;
+    const uint32_t lt = (1u << lane) - 1u;
+
+    auto row = [&](uint32_t j, uint32_t &b, uint32_t &st, uint32_t &nx) -> uint32_t { // ballot of non-empty
+        b = warp_base + j * 32u + lane;
+        st = b < bins ? __ldg(starts + (uint64_t) b * stride) : size;
+        nx = __shfl_down_sync(FULL_MASK, st, 1);
+        if (lane == 31)
+            nx = b + 1 < bins ? __ldg(starts + (uint64_t) (b + 1) * stride) : size;
+        return __ballot_sync(FULL_MASK, b < bins && nx != st);
+    };
+
+    uint32_t mine = 0; // warp-uniform
+    #pragma unroll 4
+    for (uint32_t j = 0; j < rows; ++j) {
+        uint32_t b, st, nx;
+        mine += __popc(row(j, b, st, nx));
+    }
+    if (lane == 0)
+        warp_sums[warp] = mine;
     __syncthreads();
-    for (uint32_t base = 0; base < bins; base += 1024) {
-        uint32_t b = base + tid;
-        uint32_t st = 0, sz = 0;
-        if (b < bins) {
-            st = starts[(uint64_t) b * stride];
-            uint32_t nxt = b + 1 < bins ? starts[(uint64_t) (b + 1) * stride] : size;
-            sz = nxt - st;
-        }
-        bool flag = sz > 0;
-        uint32_t ballot = __ballot_sync(FULL_MASK, flag);
-        if (lane == 0)
-            warp_sums[warp] = __popc(ballot);
-        __syncthreads();
-        uint32_t running = s_running;
-        uint32_t wsum = warp_sums[lane];
-        uint32_t wincl = wsum;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t up = __shfl_up_sync(FULL_MASK, wincl, d);
-            if (lane >= (uint32_t) d)
-                wincl += up;
-        }
-        uint32_t warp_excl = __shfl_sync(FULL_MASK, wincl - wsum, warp);
-        uint32_t total = __shfl_sync(FULL_MASK, wincl, 31);
-        if (flag) {
-            uint32_t rec = running + warp_excl + __popc(ballot & ((1u << lane) - 1));
-            ((uint4 *) records)[rec] = make_uint4(b, st, sz, 0);
-        }
-        __syncthreads();
-        if (tid == 0)
-            s_running = running + total;
-        __syncthreads();
+    uint32_t wsum = warp_sums[lane], wincl = wsum;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(FULL_MASK, wincl, d);
+        if (lane >= (uint32_t) d)
+            wincl += up;
+    }
+    uint32_t rec = __shfl_sync(FULL_MASK, wincl - wsum, warp);
+    const uint32_t total = __shfl_sync(FULL_MASK, wincl, 31);
+    #pragma unroll 4
+    for (uint32_t j = 0; j < rows; ++j) {
+        uint32_t b, st, nx;
+        const uint32_t flags = row(j, b, st, nx);
+        if ((flags >> lane) & 1u)
+            ((uint4 *) records)[rec + __popc(flags & lt)] = make_uint4(b, st, nx - st, 0);
+        rec += __popc(flags);
     }
     if (tid == 0)
-        records[4 * (size_t) bins] = s_running;
+        records[4 * (size_t) bins] = total;
+}
+
+/// starts[b] = number of keys below b = first slot of bucket b in the finished
+/// permutation, found by binary search over the permutation itself (keys are
+/// sorted along it).  For many buckets this beats a histogram of the keys, which
+/// no longer fits one shared-memory table: 26 dependent steps of two gathers per
+/// bucket against another one or two sweeps over all keys.
+__global__ void __launch_bounds__(256)
+mkperm_bounds_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ perm,
+                     uint32_t size, uint32_t index_base, uint32_t bins, uint32_t *__restrict__ starts) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bins)
+        return;
+    uint32_t lo = 0, hi = size; // first position whose key is >= b
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const uint32_t k = min(__ldg(keys + (__ldg(perm + mid) - index_base)), bins - 1);
+        if (k < b)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    starts[b] = lo;
 }
 
 // ------------------------------------------------ single sorting group: tiles
@@ -420,7 +448,7 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
                          const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
                          uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
                          uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
-                         uint32_t *__restrict__ out1, uint32_t *rk_smem) {
+                         uint32_t *__restrict__ out1, uint32_t *rk_smem, uint32_t tile) {
     constexpr uint32_t NB = 1u << BITS, WPT = NB / 2, G = WPT / 4, HALF = RK_THREADS / 2;
     constexpr uint32_t ROTM = G < HALF / 32 ? G : HALF / 32; // distinct rotations (see below)
     uint32_t *s_cnt = rk_smem;                              // NB * 256 packed counters
@@ -432,7 +460,6 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     __shared__ uint32_t s_warp[RK_THREADS / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
     const uint64_t base = (uint64_t) tile * RK_TILE;
     const uint32_t tile_count = FULL ? RK_TILE : (uint32_t) (size - base);
     const uint32_t first = tid * RK_ITEMS; // tile-local index of the thread's first key
@@ -458,7 +485,7 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
         }
     };
     load16(in0, key);
-    // a CTA that starts once this one has retired finds its keys in L2
+    // the next tile of this (persistent) CTA will find its keys in L2
     {
         const uint64_t ahead = base + (uint64_t) ahead_tiles * RK_TILE + first;
         if (ahead + RK_ITEMS <= size) {
@@ -565,6 +592,9 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     uint32_t idx[IN == RK_PAIRS ? RK_ITEMS : 1];
     if constexpr (IN == RK_PAIRS)
         load16(in1, idx);
+    // the bulk copies of the CTA's previous tile may still be reading the staging area
+    if (lane == 0)
+        bulk_wait_read<0>();
     __syncthreads();
 
     // ---- sort into the staging area (values are final: what is stored to global)
@@ -639,9 +669,6 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
         }
         write_runs(out1);
     }
-    // the staging area must outlive the bulk copies that read it
-    if (lane == 0)
-        bulk_wait_read<0>();
 }
 
 template <int BITS, int IN, int OUT>
@@ -655,10 +682,26 @@ mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__res
     static_assert(BITS >= 3 && BITS <= 6, "3..6-bit digits");
     static_assert(TWO ? OUT != RK_FINAL || IN == RK_PAIRS : OUT != RK_OUT_PAIRS, "unsupported combination");
     extern __shared__ __align__(16) uint32_t rk_smem[];
-    if ((uint64_t) (blockIdx.x + 1) * RK_TILE <= size)
-        rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem);
-    else
-        rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem);
+    if constexpr (IN == RK_RAW1) {
+        // persistent CTAs: the bulk stores of a tile drain while the next one is loaded and
+        // counted (154 vs 165 us per 2^26 keys; the variants that carry more state spill
+        // in the loop and are launched one tile per CTA)
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            if ((uint64_t) (tile + 1) * RK_TILE <= size)
+                rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
+            else
+                rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
+        }
+    } else {
+        const uint32_t tile = blockIdx.x;
+        if ((uint64_t) (tile + 1) * RK_TILE <= size)
+            rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
+        else
+            rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
+    }
+    // the staging area must outlive the bulk copies that read it
+    if ((threadIdx.x & 31) == 0)
+        bulk_wait_read<0>();
 }
 
 struct RkArgs {
@@ -675,9 +718,10 @@ static cudaError_t rk_launch_one(cudaStream_t stream, const RkArgs &a) {
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess)
         return err;
-    kernel<<<a.ntiles, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.size, a.ntiles, a.shift, a.mask,
-                                                   a.bins, a.ib, a.keymask, (uint32_t) (RK_CTAS * sm_count()),
-                                                   a.index_base, a.out0, a.out1);
+    const uint32_t resident = (uint32_t) (RK_CTAS * sm_count());
+    const uint32_t grid = IN == RK_RAW1 ? std::min<uint32_t>(a.ntiles, resident) : a.ntiles;
+    kernel<<<grid, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.size, a.ntiles, a.shift, a.mask,
+                                               a.bins, a.ib, a.keymask, resident, a.index_base, a.out0, a.out1);
     count_launch();
     return cudaGetLastError();
 }
@@ -873,10 +917,17 @@ static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint
             return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
         }
         uint32_t *records = hist + hist_words;
-        int rc = histogram_launch(stream, values, size, bucket_count, hist);
-        if (!rc)
-            rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, bucket_count,
-                                          bucket_count, 1, 0, hist, hist);
+        int rc = B200_OK;
+        if (bucket_count > 8192) {
+            mkperm_bounds_kernel<<<(uint32_t) ceil_div(bucket_count, 256), 256, 0, stream>>>(
+                values, perm, size, index_base, bucket_count, hist);
+            count_launch();
+        } else {
+            rc = histogram_launch(stream, values, size, bucket_count, hist);
+            if (!rc)
+                rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, bucket_count,
+                                              bucket_count, 1, 0, hist, hist);
+        }
         if (!rc) {
             mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(hist, 1, bucket_count, size, records);
             count_launch();
