@@ -220,13 +220,16 @@ scatter_reduce_kernel(T *__restrict__ target, const T *__restrict__ value,
                       const uint32_t *__restrict__ index, const uint8_t *__restrict__ mask,
                       uint64_t n) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
-    const uint64_t first = (uint64_t) blockIdx.x * SCATTER_THREADS + threadIdx.x;
     int path = PATH_RUNS; // warp-uniform
     uint32_t batch = 0;
 
-    // all lanes of a warp run the same number of iterations (warp collectives)
-    for (uint64_t base = first - lane; base < n; base += stride * U, ++batch) {
+    // a CTA walks tiles of U * 256 CONSECUTIVE elements (the U loads of a thread stay
+    // within one 4 - 8 KiB neighbourhood); all lanes of a warp run the same number of
+    // iterations (warp collectives)
+    constexpr uint64_t TILE = (uint64_t) SCATTER_THREADS * U;
+    for (uint64_t tile0 = (uint64_t) blockIdx.x * TILE; tile0 < n; tile0 += (uint64_t) gridDim.x * TILE, ++batch) {
+        const uint64_t base = tile0 + (threadIdx.x & ~31u);
+        constexpr uint64_t stride = SCATTER_THREADS;
         T val[U];
         uint32_t idx[U];
         bool on[U];
