@@ -191,7 +191,8 @@ template <typename T, int Op, int J, int THREADS, bool FULL> struct TileScan {
 /// THREADS compute threads (+ one look-back warp when CHAIN), tiles of
 /// THREADS * J vectors, ring of S shared-memory slots.
 template <typename T, int Op, int J, int S, int THREADS, bool CHAIN, int LB>
-__global__ void __launch_bounds__(THREADS + (CHAIN ? 32 + 32 * LB : 0), THREADS >= 512 ? 2 : 1)
+__global__ void __launch_bounds__(THREADS + (CHAIN ? 32 + 32 * LB : 0),
+                                  (THREADS >= 512 && (size_t) S * THREADS * J * 16 <= 112 * 1024) ? 2 : 1)
 scan_stream_kernel(const FastParams p) {
     using V = typename ValueOf<T>::type;
     using R = Red<V, Op>;
@@ -701,6 +702,11 @@ template <typename T, int Op> static int launch_fast(const ScanCall &c, bool *ha
             case 5: return launch_fast_g<T, Op, Geom<256, 4, 4, 1>>(c, handled);
             case 6: return launch_fast_g<T, Op, Geom<384, 4, 4, 2>>(c, handled);
             case 7: return launch_fast_g<T, Op, Geom<384, 4, 4, 1>>(c, handled);
+            case 8: return launch_fast_g<T, Op, Geom<512, 8, 2, 1>>(c, handled);
+            case 9: return launch_fast_g<T, Op, Geom<512, 8, 3, 1>>(c, handled);
+            case 10: return launch_fast_g<T, Op, Geom<768, 4, 3, 1>>(c, handled);
+            case 11: return launch_fast_g<T, Op, Geom<896, 4, 3, 1>>(c, handled);
+            case 12: return launch_fast_g<T, Op, Geom<512, 6, 3, 1>>(c, handled);
             default: break;
         }
     }

@@ -524,6 +524,112 @@ static PacketFn pick_packet(int vt, int op) {
     return nullptr;
 }
 
+/// Local / Auto for 4-byte element types with 16-byte aligned inputs: a lane loads
+/// FOUR consecutive elements (one 128-bit load per array), merges equal neighbours
+/// among its own four first, and only lanes whose four elements all hit one address
+/// take part in the warp-level run merge -- one shuffle round per 128 elements
+/// instead of per 32 (the merge is shuffle-pipe bound: ~46 cycles per round and
+/// sub-partition).  Incoherent data skip the warp stage altogether.  A periodic
+/// probe (match.any over one component) switches to scatter_local when duplicates
+/// are frequent but not adjacent (few distinct targets).
+template <typename T, int Op>
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_reduce_vec4_kernel(T *__restrict__ target, const T *__restrict__ value,
+                           const uint32_t *__restrict__ index, const uint8_t *__restrict__ mask,
+                           uint64_t nvec) {
+    static_assert(sizeof(T) == 4, "four elements per 16-byte load");
+    const uint32_t lane = threadIdx.x & 31;
+    bool use_match = false; // warp-uniform
+    uint32_t batch = 0;
+    for (uint64_t tile0 = (uint64_t) blockIdx.x * SCATTER_THREADS; tile0 < nvec;
+         tile0 += (uint64_t) gridDim.x * SCATTER_THREADS, ++batch) {
+        const uint64_t q = tile0 + threadIdx.x; // vector index (warp-uniform trip count)
+        const bool in_range = q < nvec;
+        uint32_t idx[4] = { 0, 0, 0, 0 };
+        T val[4];
+        bool on[4] = { false, false, false, false };
+        if (in_range) {
+            const uint4 i4 = ld_stream(index + 4 * q);
+            const uint4 v4 = ld_stream(value + 4 * q);
+            idx[0] = i4.x; idx[1] = i4.y; idx[2] = i4.z; idx[3] = i4.w;
+            memcpy(&val[0], &v4.x, 4); memcpy(&val[1], &v4.y, 4);
+            memcpy(&val[2], &v4.z, 4); memcpy(&val[3], &v4.w, 4);
+            uint32_t m4 = 0x01010101u;
+            if (mask)
+                m4 = __ldcs((const uint32_t *) (mask + 4 * q));
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                on[k] = ((m4 >> (8 * k)) & 0xffu) != 0;
+        }
+        const bool single = on[0] && on[1] && on[2] && on[3] && idx[0] == idx[1] && idx[1] == idx[2] &&
+                            idx[2] == idx[3];
+        const uint32_t singles = __ballot_sync(FULL_MASK, single);
+
+        if ((batch & 7) == 0) {
+            // probe: duplicates among the first components that lane coherence does not explain
+            const uint32_t active = __ballot_sync(FULL_MASK, on[0]);
+            uint32_t leaders = 0;
+            if (on[0])
+                leaders = (__match_any_sync(active, idx[0]) & ((1u << lane) - 1u)) == 0;
+            const uint32_t distinct = __popc(__ballot_sync(FULL_MASK, leaders != 0));
+            const uint32_t dup = __popc(active) - distinct;
+            use_match = dup >= 8 && __popc(singles) < 16;
+        }
+        if (use_match) {
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                scatter_local<T, Op>(target, idx[k], val[k], on[k], lane);
+            continue;
+        }
+
+        if (single) {
+            // the lane's four elements: one value
+            T v = ElemOp<T, Op>::apply(ElemOp<T, Op>::apply(val[0], val[1]), ElemOp<T, Op>::apply(val[2], val[3]));
+            val[0] = v;
+        }
+        if (singles) { // warp-uniform: runs of neighbouring single lanes with equal index
+            const uint32_t prev_idx = __shfl_up_sync(FULL_MASK, idx[0], 1);
+            const bool head = lane == 0 || !single || !((singles >> (lane - 1)) & 1u) || idx[0] != prev_idx;
+            const uint32_t heads = __ballot_sync(FULL_MASK, head);
+            if (heads != FULL_MASK) {
+                const uint32_t above = heads & ~((2u << lane) - 1u);
+                const uint32_t last = above ? (uint32_t) __ffs(above) - 2u : 31u;
+                T v = val[0];
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const T other = shfl_elem<T>(FULL_MASK, v, min(lane + d, 31u));
+                    if (lane + d <= last)
+                        v = ElemOp<T, Op>::apply(v, other);
+                }
+                val[0] = v;
+            }
+            if (single) {
+                if (head)
+                    Atomic<T, Op>::apply(target + idx[0], val[0]);
+                continue; // (lane-divergent: nothing warp-wide follows)
+            }
+        }
+        // mixed lane: merge equal neighbours among the four, one atomic per segment
+        T acc = val[0];
+        uint32_t cur = idx[0];
+        bool cur_on = on[0];
+        #pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            if (on[k] && cur_on && idx[k] == cur) {
+                acc = ElemOp<T, Op>::apply(acc, val[k]);
+            } else {
+                if (cur_on)
+                    Atomic<T, Op>::apply(target + cur, acc);
+                acc = val[k];
+                cur = idx[k];
+                cur_on = on[k];
+            }
+        }
+        if (cur_on)
+            Atomic<T, Op>::apply(target + cur, acc);
+    }
+}
+
 struct ScatterCall {
     cudaStream_t stream;
     void *target;
@@ -540,6 +646,29 @@ template <typename T, int Op> static int launch_scatter(const ScatterCall &c) {
         1, std::min<uint64_t>(ceil_div(c.n, (uint64_t) SCATTER_THREADS * U), (uint64_t) sm_count() * 16));
     T *target = (T *) c.target;
     const T *value = (const T *) c.value;
+    if constexpr (sizeof(T) == 4) {
+        // Local / Auto, 16-byte aligned inputs: four elements per lane; the (< 4) tail
+        // elements go through the scalar kernel
+        if ((c.mode == B200_MODE_LOCAL || c.mode == B200_MODE_AUTO) && c.n >= 4096 &&
+            ((uintptr_t) c.index % 16) == 0 && ((uintptr_t) c.value % 16) == 0 &&
+            (!c.mask || ((uintptr_t) c.mask % 4) == 0)) {
+            const uint64_t nvec = c.n / 4;
+            uint32_t vgrid = (uint32_t) std::max<uint64_t>(
+                1, std::min<uint64_t>(ceil_div(nvec, (uint64_t) SCATTER_THREADS), (uint64_t) sm_count() * 16));
+            scatter_reduce_vec4_kernel<T, Op><<<vgrid, SCATTER_THREADS, 0, c.stream>>>(target, value, c.index,
+                                                                                     c.mask, nvec);
+            B200_LAUNCH_CHECK();
+            if (c.n % 4 == 0)
+                return B200_OK;
+            ScatterCall tail = c;
+            tail.value = value + 4 * nvec;
+            tail.index = c.index + 4 * nvec;
+            tail.mask = c.mask ? c.mask + 4 * nvec : nullptr;
+            tail.n = c.n % 4;
+            tail.mode = B200_MODE_DIRECT;
+            return launch_scatter<T, Op>(tail);
+        }
+    }
     switch (c.mode) {
         case B200_MODE_DIRECT:
             scatter_reduce_kernel<T, Op, B200_MODE_DIRECT, false, U><<<grid, SCATTER_THREADS, 0, c.stream>>>(
