@@ -177,11 +177,11 @@ compress_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint
 // ------------------------------------------------ large masks: bit-packed tiles
 //
 // Two launches, no inter-CTA dependency inside either of them:
-//   pack     the mask is read once (1 byte per entry, 64 bytes in flight per thread)
+//   pack     the mask is read once (1 byte per entry, 128 bytes in flight per thread)
 //            and reduced to one BIT per entry; a CTA also leaves the number of set
-//            entries of its 16384-entry tile and adds it to the counter of its
+//            entries of its 32768-entry tile and adds it to the counter of its
 //            group of 128 tiles                                   (HBM: n + n / 8)
-//   expand   a CTA re-reads the 2 KiB of bits of its tile (L2 resident: the bit
+//   expand   a CTA re-reads the 4 KiB of bits of its tile (L2 resident: the bit
 //            array of a 2^28 mask is 32 MiB), sums the counters of the groups and
 //            of the tiles of its own group in front of it (<= 255 + n / 2^21 words,
 //            one or two loads per thread -- a separate scan kernel over the tile
@@ -200,13 +200,14 @@ compress_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint
 // hand-shake to wait for.
 //
 // Bit layout = the thread layout of both kernels: warp w of a tile owns entries
-// [w * 2048, (w + 1) * 2048) as four rows of 512; lane l holds one 16-bit word per
-// row (entries l * 16 .. + 15 of the row), i.e. one 8-byte {rows 0|1, rows 2|3}
-// pair per thread, stored / loaded fully coalesced.  Only bit 0 of a mask byte is
+// [w * 4096, (w + 1) * 4096) as eight rows of 512; lane l holds one 16-bit word per
+// row (entries l * 16 .. + 15 of the row), i.e. one 16-byte {rows 0|1, .., rows 6|7}
+// vector per thread, stored / loaded fully coalesced.  (Four rows per warp: the
+// fixed cost per warp -- lane scan, tile offset -- made the sparse case issue bound.)  Only bit 0 of a mask byte is
 // looked at (entries are required to be 0 or 1, jit.h:2377-2379).
 //
-// Expansion of a warp's 2048 entries (four 16-bit words per lane):
-//   dense   (> 4 * CT_SPARSE set entries): every lane appends the indices of its set
+// Expansion of a warp's 4096 entries (eight 16-bit words per lane):
+//   dense   (> 8 * CT_SPARSE set entries): every lane appends the indices of its set
 //           bits to the warp's staging area in shared memory (16 predicated stores
 //           per word, no popc / shuffle per entry), two rows at a time; the up to
 //           4 KiB then leave with ONE bulk copy shared -> global (cp.async.bulk)
@@ -220,9 +221,10 @@ compress_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint
 
 static constexpr int CT_THREADS = 256;
 static constexpr int CT_WARPS = CT_THREADS / 32;
-static constexpr int CT_ROWS = 4;                                   // rows of 512 entries per warp
-static constexpr uint32_t CT_WARP_ENTRIES = CT_ROWS * 512;          // 2048
-static constexpr uint32_t CT_TILE = CT_WARPS * CT_WARP_ENTRIES;     // 16384 entries per CTA
+static constexpr int CT_ROWS = 8;                                   // rows of 512 entries per warp
+static constexpr uint32_t CT_WARP_ENTRIES = CT_ROWS * 512;          // 4096
+static constexpr uint32_t CT_TILE = CT_WARPS * CT_WARP_ENTRIES;     // 32768 entries per CTA
+struct __align__(16) CtBits { uint32_t w[CT_ROWS / 2]; };            // a thread's bits: rows 2q | 2q + 1 << 16
 static constexpr uint32_t CT_SPARSE = 48;                           // set entries per 512-entry row
 static constexpr uint32_t CT_STAGE = 2 * 512 + 4;                   // staging words per warp (two rows)
 static constexpr uint32_t CT_GROUP_SHIFT = 7;                       // 128 tiles per counter group
@@ -241,7 +243,7 @@ B200_DEVICE uint32_t pack16(uint4 v) {
 /// array (in - mis); bits / tiles are indexed in that virtual space.
 __global__ void __launch_bounds__(CT_THREADS)
 compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis,
-                     uint2 *__restrict__ bits, uint32_t *__restrict__ counts,
+                     CtBits *__restrict__ bits, uint32_t *__restrict__ counts,
                      uint32_t *__restrict__ group_counts) {
     __shared__ uint32_t s_cnt[CT_WARPS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -272,11 +274,15 @@ compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis
             v[j] = x;
         }
     }
-    uint2 hp;
-    hp.x = pack16(v[0]) | (pack16(v[1]) << 16);
-    hp.y = pack16(v[2]) | (pack16(v[3]) << 16);
+    CtBits hp;
+    uint32_t pc = 0;
+    #pragma unroll
+    for (int q = 0; q < CT_ROWS / 2; ++q) {
+        hp.w[q] = pack16(v[2 * q]) | (pack16(v[2 * q + 1]) << 16);
+        pc += __popc(hp.w[q]);
+    }
     bits[(size_t) blockIdx.x * CT_THREADS + tid] = hp;
-    const uint32_t c = __reduce_add_sync(FULL_MASK, __popc(hp.x) + __popc(hp.y));
+    const uint32_t c = __reduce_add_sync(FULL_MASK, pc);
     if (lane == 0)
         s_cnt[warp] = c;
     __syncthreads();
@@ -291,7 +297,7 @@ compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis
 }
 
 __global__ void __launch_bounds__(CT_THREADS)
-compress_expand_kernel(const uint2 *__restrict__ bits, const uint32_t *__restrict__ counts,
+compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restrict__ counts,
                        const uint32_t *__restrict__ group_counts, uint32_t ntiles, uint32_t mis,
                        uint32_t *__restrict__ out, uint32_t *__restrict__ count_out) {
     __shared__ uint32_t s_wtot[CT_WARPS], s_before[CT_WARPS];
@@ -300,8 +306,12 @@ compress_expand_kernel(const uint2 *__restrict__ bits, const uint32_t *__restric
     const uint32_t tile = blockIdx.x;
     uint32_t *stage = ct_stage + warp * CT_STAGE;
 
-    const uint2 hp2 = __ldg(bits + (size_t) tile * CT_THREADS + tid);
-    const uint32_t hp[CT_ROWS / 2] = { hp2.x, hp2.y };
+    uint32_t hp[CT_ROWS / 2];
+    {
+        const uint4 raw = __ldg((const uint4 *) (bits + (size_t) tile * CT_THREADS + tid));
+        hp[0] = raw.x; hp[1] = raw.y; hp[2] = raw.z; hp[3] = raw.w;
+    }
+    static_assert(CT_ROWS == 8, "one 16-byte load of bits per thread");
     // set entries in front of this tile: whole groups of tiles, then the tiles of
     // this tile's own group
     uint32_t before = 0;
@@ -475,12 +485,12 @@ static int compress_tiles(cudaStream_t stream, const uint8_t *in, uint64_t size,
                           uint32_t *count_dev) {
     const uint32_t mis = (uint32_t) ((uintptr_t) in & 15);
     const uint32_t ntiles = (uint32_t) ceil_div(size + mis, CT_TILE);
-    const size_t bits_bytes = (size_t) ntiles * CT_THREADS * sizeof(uint2);
+    const size_t bits_bytes = (size_t) ntiles * CT_THREADS * sizeof(CtBits);
     const uint32_t ngroups = (ntiles >> CT_GROUP_SHIFT) + 1;
     uint8_t *scratch = (uint8_t *) temp_alloc(bits_bytes + ((size_t) ntiles + ngroups) * 4, stream);
     if (!scratch)
         return fail(B200_ERR_CUDA, "jit_compress(): out of memory (%zu bytes)", bits_bytes);
-    uint2 *bits = (uint2 *) scratch;
+    CtBits *bits = (CtBits *) scratch;
     uint32_t *counts = (uint32_t *) (scratch + bits_bytes);
     uint32_t *group_counts = counts + ntiles;
     cudaError_t err = cudaMemsetAsync(group_counts, 0, (size_t) ngroups * 4, stream);
