@@ -232,10 +232,13 @@ int b200_init(void) {
 }
 
 
+static void release_pinned_cache(); // (allocator, below)
+
 int b200_shutdown(void) {
     std::lock_guard<std::mutex> guard(g_lock);
     if (!g_initialised)
         return B200_OK;
+    release_pinned_cache();
     for (size_t i = 0; i < g_devices.size(); ++i) {
         if (g_devices[i].stream) {
             cudaSetDevice((int) i);
@@ -298,6 +301,33 @@ int b200_sync(void *stream) {
     return B200_OK;
 }
 
+// Allocator contract of the reference (src/malloc.cpp:102-306):
+// sizes are rounded up to a power of two >= 64 bytes (compress and all / any of the
+// reference rely on that padding, jit.h:2382-2383), freed blocks are cached, and
+// allocation / release are ordered on the device's stream instead of synchronising
+// the device.  Device memory: the CUDA stream-ordered pool of the library stream
+// (release threshold raised in retain_pool(), so freed blocks stay cached).  Pinned
+// host memory: a free list per size; a block is handed out again once the event
+// recorded at its release has completed.
+struct PinnedBlock {
+    void *ptr;
+    cudaEvent_t released;
+};
+static std::unordered_map<size_t, std::vector<PinnedBlock>> g_pinned_cache;
+// pointer -> rounded size (pinned blocks only)
+static std::unordered_map<void *, size_t> g_pinned_size;
+
+static void release_pinned_cache() { // g_lock held
+    for (auto &kv : g_pinned_cache) {
+        for (PinnedBlock &b : kv.second) {
+            cudaEventSynchronize(b.released);
+            cudaEventDestroy(b.released);
+            cudaFreeHost(b.ptr);
+        }
+    }
+    g_pinned_cache.clear();
+}
+
 void *b200_malloc(size_t size, int kind) {
     if (ensure_init() || size == 0)
         return nullptr;
@@ -307,9 +337,37 @@ void *b200_malloc(size_t size, int kind) {
     while (rounded < size)
         rounded <<= 1;
     void *ptr = nullptr;
-    cudaError_t err = kind == 1 ? cudaMallocHost(&ptr, rounded) : cudaMalloc(&ptr, rounded);
+    if (kind == 1) {
+        {
+            std::lock_guard<std::mutex> guard(g_lock);
+            auto &list = g_pinned_cache[rounded];
+            for (size_t i = 0; i < list.size(); ++i) {
+                if (cudaEventQuery(list[i].released) == cudaSuccess) {
+                    ptr = list[i].ptr;
+                    cudaEventDestroy(list[i].released);
+                    list.erase(list.begin() + i);
+                    break;
+                }
+            }
+            cudaGetLastError(); // cudaErrorNotReady from the queries
+        }
+        if (!ptr) {
+            cudaError_t err = cudaMallocHost(&ptr, rounded);
+            if (err != cudaSuccess) {
+                cuda_fail(err, "cudaMallocHost");
+                return nullptr;
+            }
+        }
+        std::lock_guard<std::mutex> guard(g_lock);
+        g_allocs[ptr] = kind;
+        g_pinned_size[ptr] = rounded;
+        return ptr;
+    }
+    cudaStream_t s = (cudaStream_t) b200_stream();
+    retain_pool(current_device());
+    cudaError_t err = cudaMallocAsync(&ptr, rounded, s);
     if (err != cudaSuccess) {
-        cuda_fail(err, kind == 1 ? "cudaMallocHost" : "cudaMalloc");
+        cuda_fail(err, "cudaMallocAsync");
         return nullptr;
     }
     std::lock_guard<std::mutex> guard(g_lock);
@@ -321,6 +379,7 @@ int b200_free(void *ptr) {
     if (!ptr)
         return B200_OK;
     int kind = -1;
+    size_t pinned_size = 0;
     {
         std::lock_guard<std::mutex> guard(g_lock);
         auto it = g_allocs.find(ptr);
@@ -328,11 +387,22 @@ int b200_free(void *ptr) {
             return fail(B200_ERR_INVALID, "b200_free(): unknown address %p!", ptr);
         kind = it->second;
         g_allocs.erase(it);
+        if (kind == 1) {
+            pinned_size = g_pinned_size[ptr];
+            g_pinned_size.erase(ptr);
+        }
     }
-    if (kind == 1)
-        B200_CUDA_CHECK(cudaFreeHost(ptr));
-    else
-        B200_CUDA_CHECK(cudaFree(ptr));
+    cudaStream_t s = (cudaStream_t) b200_stream();
+    if (kind == 1) {
+        // reusable once the work enqueued so far (which may still read / write it) is done
+        cudaEvent_t ev;
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventRecord(ev, s));
+        std::lock_guard<std::mutex> guard(g_lock);
+        g_pinned_cache[pinned_size].push_back({ ptr, ev });
+    } else {
+        B200_CUDA_CHECK(cudaFreeAsync(ptr, s));
+    }
     return B200_OK;
 }
 
