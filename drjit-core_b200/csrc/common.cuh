@@ -248,11 +248,11 @@ template <typename V, int Op> B200_DEVICE V warp_reduce(V v, int width = 32) {
 //
 // One 64-bit word carries {status, 32-bit payload} and is published / observed
 // with a single relaxed gpu-scope access, so no fence is needed between value
-// and flag.  64-bit payloads use two such words (low / high half, each tagged
-// with the status); a reader accepts them only when both tags agree, which is
-// safe because a tile's AGGREGATE is written before -- and never after -- its
-// PREFIX.  (The reference uses ld.volatile / st.cg status+value pairs,
-// resources/common.h:180-255.)
+// and flag.  64-bit payloads use one 16-byte {value, status} pair, published /
+// observed with ONE 128-bit relaxed access (st / ld.relaxed.gpu.global.b128 ->
+// STG / LDG.E.128.STRONG.GPU): a reader never sees a torn pair and does not have
+// to re-poll until two tags agree.  (The reference uses ld.volatile / st.cg
+// status+value pairs, resources/common.h:180-255.)
 
 enum : uint32_t { DESC_INVALID = 0, DESC_AGGREGATE = 1, DESC_PREFIX = 2 };
 
@@ -264,6 +264,17 @@ B200_DEVICE uint64_t ld_relaxed_u64(const uint64_t *ptr) {
     uint64_t v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
     return v;
+}
+
+/// 16-byte aligned, single-copy atomic 128-bit store / load
+B200_DEVICE void st_relaxed_b128(uint64_t *ptr, uint64_t lo, uint64_t hi) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}"
+                 :: "l"(ptr), "l"(lo), "l"(hi) : "memory");
+}
+
+B200_DEVICE void ld_relaxed_b128(const uint64_t *ptr, uint64_t &lo, uint64_t &hi) {
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(lo), "=l"(hi) : "l"(ptr) : "memory");
 }
 
 template <typename V> struct Desc {
@@ -278,8 +289,7 @@ template <typename V> struct Desc {
         } else {
             uint64_t bits;
             memcpy(&bits, &value, 8);
-            st_relaxed_u64(p,     ((uint64_t) status << 32) | (uint32_t) bits);
-            st_relaxed_u64(p + 1, ((uint64_t) status << 32) | (uint32_t) (bits >> 32));
+            st_relaxed_b128(p, bits, (uint64_t) status);
         }
     }
 
@@ -292,11 +302,10 @@ template <typename V> struct Desc {
             memcpy(&value, &bits, sizeof(V));
             return (uint32_t) (w >> 32);
         } else {
-            uint64_t w0 = ld_relaxed_u64(p), w1 = ld_relaxed_u64(p + 1);
-            uint32_t s0 = (uint32_t) (w0 >> 32), s1 = (uint32_t) (w1 >> 32);
-            uint64_t bits = ((uint64_t) (uint32_t) w1 << 32) | (uint32_t) w0;
+            uint64_t bits, st;
+            ld_relaxed_b128(p, bits, st);
             memcpy(&value, &bits, 8);
-            return s0 == s1 ? s0 : DESC_INVALID;
+            return (uint32_t) st;
         }
     }
 };
