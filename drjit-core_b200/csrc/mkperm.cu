@@ -320,15 +320,42 @@ B200_DEVICE uint32_t mt_digit(uint32_t key, uint32_t shift, uint32_t mask, uint3
     return min((key >> shift) & mask, bins - 1); // out-of-range keys must not corrupt memory
 }
 
-/// table[d * ntiles + tile] = number of keys of the tile whose digit is d.  A CTA
+/// table[table_index(tile, d)] = number of keys of the tile whose digit is d.  A CTA
 /// counts MT_GROUP consecutive tiles into one shared-memory histogram each, so
 /// that the MT_GROUP entries of a digit are contiguous in the digit-major table
 /// (one 32-byte run instead of MT_GROUP scattered words).
 /// Dynamic shared memory: MT_GROUP * bins counters.
 static constexpr uint32_t MT_GROUP = 8;
 
+/// Tiles of the ranked path never cross a sorting group: group g owns the tiles
+/// [g * tpg, (g + 1) * tpg), the last tile of a group may be short.  One group:
+/// group_size = size, tpg = number of tiles.
+struct TileGeom {
+    uint64_t size;        // keys in total
+    uint32_t group_size;  // keys per sorting group
+    uint32_t tpg;         // tiles per group
+    uint32_t ntiles;      // tiles in total
+};
+
+/// First key and number of keys of a tile
+B200_DEVICE void tile_range(const TileGeom &g, uint32_t tile, uint64_t &base, uint32_t &count) {
+    const uint32_t grp = tile / g.tpg, tg = tile - grp * g.tpg;
+    const uint64_t gstart = (uint64_t) grp * g.group_size;
+    const uint64_t gend = min(gstart + g.group_size, g.size);
+    base = gstart + (uint64_t) tg * MT_TILE;
+    count = base < gend ? (uint32_t) min((uint64_t) MT_TILE, gend - base) : 0u;
+}
+
+/// Position of (tile, digit) in the count table: [group][digit][tile of the group],
+/// so that an exclusive scan in blocks of bins * tpg entries yields the first
+/// output slot of every (digit, tile) pair relative to its group.
+B200_DEVICE uint64_t table_index(const TileGeom &g, uint32_t tile, uint32_t digit, uint32_t bins) {
+    const uint32_t grp = tile / g.tpg, tg = tile - grp * g.tpg;
+    return ((uint64_t) grp * bins + digit) * g.tpg + tg;
+}
+
 __global__ void __launch_bounds__(MT_THREADS)
-mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32_t ntiles,
+mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, const TileGeom g,
                         uint32_t shift, uint32_t mask, uint32_t bins,
                         uint32_t *__restrict__ table) {
     extern __shared__ uint32_t mk_smem[];
@@ -337,18 +364,22 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32
     for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS)
         mk_smem[i] = 0;
     __syncthreads();
-    const bool aligned = ((uintptr_t) keys & 15) == 0;
     #pragma unroll 1
     for (uint32_t t = 0; t < MT_GROUP; t += 2) {
         // two tiles per step: 8 x 16-byte loads in flight per thread
         uint4 k4[2][MT_ITEMS / 4];
         bool full[2];
+        uint64_t base[2];
+        uint32_t count[2];
         #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const uint64_t base = (uint64_t) (tile0 + t + u) * MT_TILE;
-            full[u] = aligned && base + MT_TILE <= size;
+            base[u] = 0;
+            count[u] = 0;
+            if (tile0 + t + u < g.ntiles)
+                tile_range(g, tile0 + t + u, base[u], count[u]);
+            full[u] = count[u] == MT_TILE && ((uintptr_t) (keys + base[u]) & 15) == 0;
             if (full[u]) {
-                const uint4 *v = (const uint4 *) (keys + base);
+                const uint4 *v = (const uint4 *) (keys + base[u]);
                 #pragma unroll
                 for (int j = 0; j < MT_ITEMS / 4; ++j)
                     k4[u][j] = ld_stream(v + j * MT_THREADS + tid);
@@ -357,7 +388,6 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32
         #pragma unroll
         for (int u = 0; u < 2; ++u) {
             uint32_t *h = mk_smem + (t + u) * bins;
-            const uint64_t base = (uint64_t) (tile0 + t + u) * MT_TILE;
             if (full[u]) {
                 #pragma unroll
                 for (int j = 0; j < MT_ITEMS / 4; ++j) {
@@ -366,12 +396,12 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32
                     atomicAdd(&h[mt_digit(k4[u][j].z, shift, mask, bins)], 1u);
                     atomicAdd(&h[mt_digit(k4[u][j].w, shift, mask, bins)], 1u);
                 }
-            } else if (base < size) {
+            } else if (count[u]) {
                 #pragma unroll 4
                 for (int j = 0; j < MT_ITEMS; ++j) {
-                    const uint64_t g = base + (uint64_t) j * MT_THREADS + tid;
-                    if (g < size)
-                        atomicAdd(&h[mt_digit(__ldg(keys + g), shift, mask, bins)], 1u);
+                    const uint32_t i = (uint32_t) j * MT_THREADS + tid;
+                    if (i < count[u])
+                        atomicAdd(&h[mt_digit(__ldg(keys + base[u] + i), shift, mask, bins)], 1u);
                 }
             }
         }
@@ -379,8 +409,8 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, uint64_t size, uint32
     __syncthreads();
     for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS) {
         const uint32_t d = i / MT_GROUP, t = i % MT_GROUP;
-        if (tile0 + t < ntiles)
-            table[(uint64_t) d * ntiles + tile0 + t] = mk_smem[t * bins + d];
+        if (tile0 + t < g.ntiles)
+            table[table_index(g, tile0 + t, d, bins)] = mk_smem[t * bins + d];
     }
 }
 
@@ -445,7 +475,8 @@ template <int BITS> constexpr size_t rk_smem_bytes() {
 /// there is no per-element store loop.
 template <int BITS, int IN, int OUT, bool FULL>
 B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
-                         const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
+                         const uint32_t *__restrict__ table, const TileGeom &geom, uint64_t base,
+                         uint32_t tile_count_in,
                          uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
                          uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
                          uint32_t *__restrict__ out1, uint32_t *rk_smem, uint32_t tile) {
@@ -460,8 +491,9 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     __shared__ uint32_t s_warp[RK_THREADS / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t base = (uint64_t) tile * RK_TILE;
-    const uint32_t tile_count = FULL ? RK_TILE : (uint32_t) (size - base);
+    const uint32_t tile_count = FULL ? RK_TILE : tile_count_in;
+    // first output slot of the tile's sorting group
+    const uint32_t group_start = (tile / geom.tpg) * geom.group_size;
     const uint32_t first = tid * RK_ITEMS; // tile-local index of the thread's first key
 
     #pragma unroll
@@ -471,7 +503,7 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     // ---- load (blocked: 64 contiguous bytes per thread)
     uint32_t key[RK_ITEMS];
     auto load16 = [&](const uint32_t *src, uint32_t (&dst)[RK_ITEMS]) {
-        if (FULL && ((uintptr_t) src & 15) == 0) {
+        if (FULL && ((uintptr_t) (src + base) & 15) == 0) {
             const uint4 *v = (const uint4 *) (src + base) + tid * (RK_ITEMS / 4);
             #pragma unroll
             for (int q = 0; q < RK_ITEMS / 4; ++q) {
@@ -486,18 +518,20 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     };
     load16(in0, key);
     // the next tile of this (persistent) CTA will find its keys in L2
-    {
-        const uint64_t ahead = base + (uint64_t) ahead_tiles * RK_TILE + first;
-        if (ahead + RK_ITEMS <= size) {
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(in0 + ahead));
+    if (tile + ahead_tiles < geom.ntiles) {
+        uint64_t abase;
+        uint32_t acount;
+        tile_range(geom, tile + ahead_tiles, abase, acount);
+        if (first + RK_ITEMS <= acount) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(in0 + abase + first));
             if constexpr (IN == RK_PAIRS)
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(in1 + ahead));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(in1 + abase + first));
         }
     }
     // first output slot of this tile's keys with digit (tid % bins): run tid
     uint32_t gstart = 0;
     if (tid < 2 * bins)
-        gstart = __ldg(table + (uint64_t) (tid < bins ? tid : tid - bins) * ntiles + tile);
+        gstart = group_start + __ldg(table + table_index(geom, tile, tid < bins ? tid : tid - bins, bins));
 
     // The scan below has thread t' rake the WPT consecutive words [t' * WPT, (t' + 1)
     // * WPT) with 128-bit accesses; rotating the 16-byte groups of a thread's segment
@@ -674,7 +708,7 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
 template <int BITS, int IN, int OUT>
 __global__ void __launch_bounds__(RK_THREADS, RK_CTAS)
 mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
-                         const uint32_t *__restrict__ table, uint64_t size, uint32_t ntiles,
+                         const uint32_t *__restrict__ table, const TileGeom geom,
                          uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
                          uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
                          uint32_t *__restrict__ out1) {
@@ -682,22 +716,25 @@ mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__res
     static_assert(BITS >= 3 && BITS <= 6, "3..6-bit digits");
     static_assert(TWO ? OUT != RK_FINAL || IN == RK_PAIRS : OUT != RK_OUT_PAIRS, "unsupported combination");
     extern __shared__ __align__(16) uint32_t rk_smem[];
+    auto one_tile = [&](uint32_t tile) {
+        uint64_t base;
+        uint32_t count;
+        tile_range(geom, tile, base, count);
+        if (count == RK_TILE)
+            rk_tile<BITS, IN, OUT, true>(in0, in1, table, geom, base, count, shift, mask, bins, ib, keymask,
+                                         ahead_tiles, index_base, out0, out1, rk_smem, tile);
+        else if (count) // block-uniform
+            rk_tile<BITS, IN, OUT, false>(in0, in1, table, geom, base, count, shift, mask, bins, ib, keymask,
+                                          ahead_tiles, index_base, out0, out1, rk_smem, tile);
+    };
     if constexpr (IN == RK_RAW1) {
         // persistent CTAs: the bulk stores of a tile drain while the next one is loaded and
         // counted (154 vs 165 us per 2^26 keys; the variants that carry more state spill
         // in the loop and are launched one tile per CTA)
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if ((uint64_t) (tile + 1) * RK_TILE <= size)
-                rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
-            else
-                rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
-        }
+        for (uint32_t tile = blockIdx.x; tile < geom.ntiles; tile += gridDim.x)
+            one_tile(tile);
     } else {
-        const uint32_t tile = blockIdx.x;
-        if ((uint64_t) (tile + 1) * RK_TILE <= size)
-            rk_tile<BITS, IN, OUT, true>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
-        else
-            rk_tile<BITS, IN, OUT, false>(in0, in1, table, size, ntiles, shift, mask, bins, ib, keymask, ahead_tiles, index_base, out0, out1, rk_smem, tile);
+        one_tile(blockIdx.x);
     }
     // the staging area must outlive the bulk copies that read it
     if ((threadIdx.x & 31) == 0)
@@ -706,8 +743,8 @@ mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__res
 
 struct RkArgs {
     const uint32_t *in0, *in1, *table;
-    uint64_t size;
-    uint32_t ntiles, shift, mask, bins, ib, keymask, index_base;
+    TileGeom geom;
+    uint32_t shift, mask, bins, ib, keymask, index_base;
     uint32_t *out0, *out1;
 };
 
@@ -719,8 +756,8 @@ static cudaError_t rk_launch_one(cudaStream_t stream, const RkArgs &a) {
     if (err != cudaSuccess)
         return err;
     const uint32_t resident = (uint32_t) (RK_CTAS * sm_count());
-    const uint32_t grid = IN == RK_RAW1 ? std::min<uint32_t>(a.ntiles, resident) : a.ntiles;
-    kernel<<<grid, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.size, a.ntiles, a.shift, a.mask,
+    const uint32_t grid = IN == RK_RAW1 ? std::min<uint32_t>(a.geom.ntiles, resident) : a.geom.ntiles;
+    kernel<<<grid, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.geom, a.shift, a.mask,
                                                a.bins, a.ib, a.keymask, resident, a.index_base, a.out0, a.out1);
     count_launch();
     return cudaGetLastError();
@@ -791,9 +828,11 @@ static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t 
                             uint32_t bins, uint32_t *hist);
 
 /// block_size == size: ranked tile passes (see mkperm_rank_place_kernel)
-static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint32_t size,
-                               uint32_t bucket_count, uint32_t *perm, uint32_t *offsets,
-                               uint32_t index_base = 0) {
+/// Ranked-tile sort of every group of 'group_size' consecutive keys (group_size ==
+/// size: one group, the vcall case).  offsets: single group only.
+static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t size, uint32_t group_size,
+                         uint32_t bucket_count, uint32_t *perm, uint32_t *offsets) {
+    const uint32_t index_base = 0;
     uint32_t total_bits = 1;
     while (total_bits < 32 && (1ull << total_bits) < bucket_count)
         total_bits++;
@@ -801,7 +840,15 @@ static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint
     while (ib < 32 && (1ull << ib) < (uint64_t) index_base + size)
         ib++;
     const uint32_t npasses = (total_bits + 5) / 6;
-    const uint32_t ntiles = (uint32_t) ceil_div(size, RK_TILE);
+    TileGeom geom{};
+    geom.size = size;
+    geom.group_size = group_size;
+    geom.tpg = (uint32_t) ceil_div(group_size, RK_TILE);
+    const uint64_t ngroups = ceil_div(size, group_size);
+    if (ngroups * geom.tpg > 0x7fffffffull)
+        return fail(B200_ERR_INVALID, "jit_block_mkperm(): too many tiles!");
+    geom.ntiles = (uint32_t) (ngroups * geom.tpg);
+    const uint32_t ntiles = geom.ntiles;
     const uint32_t keymask = total_bits >= 32 ? 0xffffffffu : (1u << total_bits) - 1u;
 
     // digit widths: as even as possible, wider digits last (a wide digit costs
@@ -833,8 +880,7 @@ static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint
         a.in0 = in0;
         a.in1 = in1;
         a.table = table;
-        a.size = size;
-        a.ntiles = ntiles;
+        a.geom = geom;
         a.ib = ib;
         a.keymask = keymask;
         a.index_base = index_base;
@@ -872,16 +918,17 @@ static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint
         const uint64_t ncounts = (uint64_t) a.bins * ntiles;
         mkperm_tile_hist_kernel<<<(uint32_t) ceil_div(ntiles, MT_GROUP), MT_THREADS,
                                   (size_t) MT_GROUP * a.bins * 4, stream>>>(
-            in0, size, ntiles, a.shift, a.mask, a.bins, table);
+            in0, geom, a.shift, a.mask, a.bins, table);
         count_launch();
-        int rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts, ncounts, 1, 0,
-                                          table, table);
+        // one exclusive scan per group over its [digit][tile] counts
+        int rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts,
+                                          (uint64_t) a.bins * geom.tpg, 1, 0, table, table);
         if (rc) {
             cleanup();
             return rc;
         }
         // single pass: bucket starts are a strided view of the scanned table
-        if (npasses == 1 && offsets) {
+        if (npasses == 1 && offsets && ngroups == 1) {
             uint32_t *records = (uint32_t *) temp_alloc(((size_t) bucket_count * 4 + 1) * 4, stream);
             if (!records) {
                 cleanup();
@@ -909,7 +956,7 @@ static int mkperm_single_group(cudaStream_t stream, const uint32_t *values, uint
     }
 
     // several passes: bucket sizes come from a whole-array histogram of the full key
-    if (npasses > 1 && offsets) {
+    if (npasses > 1 && offsets && ngroups == 1) {
         size_t hist_words = ((size_t) bucket_count + 3) & ~(size_t) 3; // keep records 16-byte aligned
         uint32_t *hist = (uint32_t *) temp_alloc((hist_words + (size_t) bucket_count * 4 + 1) * 4, stream);
         if (!hist) {
@@ -991,29 +1038,18 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     const int sms = sm_count();
     const uint64_t ngroups = ceil_div(size, block_size);
 
-    if (ngroups == 1) {
-        rc = mkperm_single_group(stream, values, size, bucket_count, perm, offsets);
+    // one sorting group (vectorised method dispatch) or groups of at least half a tile:
+    // ranked tiles.  Smaller groups would leave the tiles mostly empty: row kernels.
+    if (ngroups == 1 || block_size >= RK_TILE / 2) {
+        rc = mkperm_ranked(stream, values, size, block_size, bucket_count, perm,
+                           ngroups == 1 ? offsets : nullptr);
         if (rc)
             return rc;
-        if (offsets) {
+        if (offsets && ngroups == 1) {
             // the reference waits on an event here (src/cuda_ts.cpp:964-967)
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
             if (unique)
                 *unique = offsets[4 * (size_t) bucket_count];
-        }
-        return B200_OK;
-    }
-
-    // several LARGE sorting groups: one ranked-tile sort per group (the row kernels
-    // below rank with match.any, 256 issue cycles per warp instruction on B200)
-    if (ngroups <= 64 && block_size >= (1u << 17)) {
-        for (uint64_t g = 0; g < ngroups; ++g) {
-            const uint64_t start = g * block_size;
-            const uint32_t len = (uint32_t) std::min<uint64_t>(block_size, size - start);
-            rc = mkperm_single_group(stream, values + start, len, bucket_count, perm + start, nullptr,
-                                     (uint32_t) start);
-            if (rc)
-                return rc;
         }
         return B200_OK;
     }

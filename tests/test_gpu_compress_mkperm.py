@@ -155,7 +155,9 @@ def test_mkperm_blocked(dr, O):
     for size, bs, buckets in ((100000, 1000, 16), (100000, 12500, 300), (65536, 4096, 7),
                               (99999, 333, 40), (99999, 50000, 3000), (1000, 1, 5), (1000, 2, 5),
                               (250000, 33333, 100000),
-                              # large groups: one ranked-tile sort per group, global indices
+                              # groups of at least half a tile: segmented ranked tiles
+                              (100000, 4096, 16), (100000, 8192, 70), (100001, 8193, 5000), (300000, 4100, 3),
+                              (1 << 20, 1 << 14, 1 << 16),
                               (1 << 20, 1 << 18, 16), (1500000, 400000, 1000), (3000001, 1 << 17, 70000)):
         k = key_input(size, buckets)
         perm, offs, uq = run_mkperm(dr, k, bs, buckets)
