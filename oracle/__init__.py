@@ -288,6 +288,9 @@ class ReferenceCUDA:
         L.refcuda_all.argtypes = [vp, u32, ctypes.POINTER(i32)]
         L.refcuda_any.argtypes = [vp, u32, ctypes.POINTER(i32)]
         L.refcuda_can_scatter_reduce.argtypes = [i32, i32]
+        L.refcuda_scatter_inc.argtypes = [vp, ctypes.c_size_t, vp, vp, ctypes.c_size_t, vp]
+        L.refcuda_scatter_packet.argtypes = [i32, i32, i32, vp, ctypes.c_size_t, ctypes.POINTER(vp),
+                                             ctypes.c_size_t, vp, vp, ctypes.c_size_t]
         if L.refcuda_init():
             raise RuntimeError(L.refcuda_last_error().decode())
 
@@ -328,6 +331,14 @@ class ReferenceCUDA:
 
     def can_scatter_reduce(self, vt, op):
         return bool(self.lib.refcuda_can_scatter_reduce(vt, op))
+
+    def scatter_inc(self, d_target, target_size, d_index, d_mask, n, d_out):
+        self._check(self.lib.refcuda_scatter_inc(d_target, target_size, d_index, d_mask, n, d_out))
+
+    def scatter_packet(self, vt, op, mode, d_target, target_size, d_values, d_index, d_mask, n):
+        ptrs = (ctypes.c_void_p * len(d_values))(*d_values)
+        self._check(self.lib.refcuda_scatter_packet(vt, op, mode, d_target, target_size, ptrs,
+                                                    len(d_values), d_index, d_mask, n))
 
     def all(self, d_mask, size):
         r = ctypes.c_int(0)

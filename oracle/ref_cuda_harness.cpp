@@ -135,6 +135,71 @@ REF_API int refcuda_scatter_reduce(int vt, int op, int mode, void *target, size_
     }
 }
 
+/// out[i] = target[index[i]]++ through the reference's JIT (jit_var_scatter_inc,
+/// jit.h:1125-1143; PTX from src/cuda_scatter.cpp:356-393)
+REF_API int refcuda_scatter_inc(uint32_t *target, size_t target_size, const uint32_t *index,
+                                const uint8_t *mask, size_t n, uint32_t *out) {
+    try {
+        uint32_t t = jit_var_mem_map(JitBackend::CUDA, VarType::UInt32, target, target_size, 0);
+        uint32_t i = jit_var_mem_map(JitBackend::CUDA, VarType::UInt32, (void *) index, n, 0);
+        uint32_t m = mask ? jit_var_mem_map(JitBackend::CUDA, VarType::Bool, (void *) mask, n, 0)
+                          : jit_var_bool(JitBackend::CUDA, true);
+        uint32_t r = jit_var_scatter_inc(&t, i, m);
+        jit_var_eval(r);
+        jit_eval();
+        void *ptr = nullptr;
+        uint32_t r2 = jit_var_data(r, &ptr);
+        jit_memcpy(JitBackend::CUDA, out, ptr, n * sizeof(uint32_t));
+        jit_var_dec_ref(r2);
+        uint32_t t2 = jit_var_data(t, &ptr);
+        if (ptr != target) // the JIT decided to work on a copy
+            jit_memcpy(JitBackend::CUDA, target, ptr, target_size * sizeof(uint32_t));
+        jit_var_dec_ref(t2);
+        jit_var_dec_ref(r);
+        jit_var_dec_ref(t);
+        jit_var_dec_ref(i);
+        jit_var_dec_ref(m);
+        return 0;
+    } catch (const std::exception &e) {
+        strncpy(ref_error, e.what(), sizeof(ref_error) - 1);
+        return 1;
+    }
+}
+
+/// target[index[i] * width + k] op= values[k][i] through the reference's JIT
+/// (jit_var_scatter_packet, jit.h:1117; PTX from src/cuda_packet.cpp:169-327)
+REF_API int refcuda_scatter_packet(int vt, int op, int mode, void *target, size_t target_size,
+                                   const void *const *values, size_t width, const uint32_t *index,
+                                   const uint8_t *mask, size_t n) {
+    try {
+        uint32_t t = jit_var_mem_map(JitBackend::CUDA, (VarType) vt, target, target_size, 0);
+        uint32_t vals[16];
+        for (size_t k = 0; k < width; ++k)
+            vals[k] = jit_var_mem_map(JitBackend::CUDA, (VarType) vt, (void *) values[k], n, 0);
+        uint32_t i = jit_var_mem_map(JitBackend::CUDA, VarType::UInt32, (void *) index, n, 0);
+        uint32_t m = mask ? jit_var_mem_map(JitBackend::CUDA, VarType::Bool, (void *) mask, n, 0)
+                          : jit_var_bool(JitBackend::CUDA, true);
+        uint32_t t2 = jit_var_scatter_packet(width, t, vals, i, m, (ReduceOp) op, (ReduceMode) mode);
+        jit_var_dec_ref(t);
+        t = t2;
+        jit_eval();
+        void *ptr = nullptr;
+        uint32_t t3 = jit_var_data(t, &ptr);
+        if (ptr != target)
+            jit_memcpy(JitBackend::CUDA, target, ptr, target_size * jit_type_size((VarType) vt));
+        jit_var_dec_ref(t3);
+        jit_var_dec_ref(t);
+        for (size_t k = 0; k < width; ++k)
+            jit_var_dec_ref(vals[k]);
+        jit_var_dec_ref(i);
+        jit_var_dec_ref(m);
+        return 0;
+    } catch (const std::exception &e) {
+        strncpy(ref_error, e.what(), sizeof(ref_error) - 1);
+        return 1;
+    }
+}
+
 REF_API int refcuda_can_scatter_reduce(int vt, int op) {
     return jit_can_scatter_reduce(JitBackend::CUDA, (VarType) vt, (ReduceOp) op);
 }

@@ -205,6 +205,72 @@ def test_scatter_vs_reference_cuda(dr, R, tname, opn):
     assert not bad, bad[:10]
 
 
+def test_scatter_inc_vs_reference_cuda(dr, R):
+    # jit_var_scatter_inc through the reference's JIT vs b200_scatter_inc: which entry
+    # of a counter gets which old value is unspecified on both sides, so both results
+    # must satisfy the contract (oracle.scatter_inc_check) and leave the SAME counters
+    O = oracle.Oracle()
+    bad = []
+    for n, m in ((1000, 1), (100003, 7), (1 << 20, 1 << 10)):
+        mask = (fmix32(u32_input(n)) & np.uint32(3) != 0).astype(np.uint8)
+        before = (fmix32(np.arange(m, dtype=np.uint32)) & np.uint32(0xffff)).astype(np.uint32)
+        for kind in ("random", "coherent"):
+            idx = _index(n, m, kind)
+            d_i, d_m = to_dev(idx), to_dev(mask)
+            for mk, hmask in ((None, None), (d_m, mask)):
+                d_a, d_b = to_dev(before), to_dev(before)
+                o_a, o_b = empty_dev(n, np.uint32), empty_dev(n, np.uint32)
+                dr.scatter_inc(d_a, d_i, mk, o_a, n)
+                ref_call(R, R.scatter_inc, d_b.data_ptr(), m, d_i.data_ptr(),
+                         None if mk is None else mk.data_ptr(), n, o_b.data_ptr())
+                a, b = to_host(d_a, np.uint32), to_host(d_b, np.uint32)
+                va = O.scatter_inc_check(before, a, idx, hmask, to_host(o_a, np.uint32))
+                ob = to_host(o_b, np.uint32).copy()
+                if hmask is not None:
+                    ob[hmask == 0] = 0  # undefined in the reference (jit.h:1136)
+                vb = O.scatter_inc_check(before, b, idx, hmask, ob)
+                if va or vb or not np.array_equal(a, b):
+                    bad.append((n, m, kind, mk is not None, va, vb))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("width", [2, 4])
+def test_scatter_packet_vs_reference_cuda(dr, R, width):
+    # jit_var_scatter_packet (reducing) through the reference's JIT vs
+    # b200_scatter_reduce_packet: u32 bit-exact, f32 Add within FP32_TOL, f32 Max exact
+    bad = []
+    for n, m in ((1000, 7), (100003, 997), (1 << 20, 1 << 14)):
+        mask = (fmix32(u32_input(n)) & np.uint32(3) != 0).astype(np.uint8)
+        for kind in ("random", "coherent"):
+            idx = _index(n, m, kind)
+            d_i, d_m = to_dev(idx), to_dev(mask)
+            for tname, opn in (("u32", "add"), ("u32", "max"), ("f32", "add"), ("f32", "max")):
+                vt, op = VT[tname], OP[opn]
+                dt = oracle.NP_OF_VT[vt]
+                if tname == "u32":
+                    vals = [(u32_input(n) >> np.uint32(8 + k)).astype(np.uint32) for k in range(width)]
+                else:
+                    vals = [(f32_input(n) + np.float32(k) - np.float32(0.5 if opn == "max" else 0.0)).astype(np.float32)
+                            for k in range(width)]
+                ident = oracle.Oracle().reduce_identity(vt, op)
+                tgt = np.full(m * width, ident & 0xFFFFFFFF, dtype=np.uint32).view(dt)
+                d_vals = [to_dev(v) for v in vals]
+                for mk in (None, d_m):
+                    for mode in (0, 1):
+                        d_a, d_b = to_dev(tgt), to_dev(tgt)
+                        dr.scatter_reduce_packet(vt, op, d_a, d_vals, d_i, mk, n, mode=mode)
+                        ref_call(R, R.scatter_packet, vt, op, mode, d_b.data_ptr(), m * width,
+                                 [v.data_ptr() for v in d_vals], d_i.data_ptr(),
+                                 None if mk is None else mk.data_ptr(), n)
+                        a, b = to_host(d_a, dt), to_host(d_b, dt)
+                        if tname == "f32" and opn == "add":
+                            if rel_err(a, b) > FP32_TOL:
+                                bad.append((n, m, kind, tname, opn, mode, mk is not None, rel_err(a, b)))
+                        elif not np.array_equal(a, b):
+                            bad.append((n, m, kind, tname, opn, mode, mk is not None))
+    assert not bad, bad[:10]
+
+
 def test_all_any_vs_reference_cuda(dr, R):
     for size in (1, 3, 4, 5, 1000, 1 << 20):
         for fill in (0, 1):
