@@ -678,6 +678,17 @@ def measure_sharded(torch, dr, dist, sh, world, rank, dev, peak, barrier):
                      "frac_of_n_gpu_peak": gbs / (peak * world)}
     torch.cuda.synchronize()
     res["reduce_value"] = float(res_buf[0].item())
+    # sanity of the sharded exclusive scan (not a parity test -- those are in tests/):
+    # the last element of the last shard plus the last input is the global sum
+    last = torch.zeros(2, dtype=torch.float64, device=dev)
+    if rank == world - 1:
+        last[0] = out[-1].double() + x[-1].double()
+        last[1] = 1.0
+    if world > 1:
+        dist.all_reduce(last, op=dist.ReduceOp.SUM)
+    res["scan_last_plus_input"] = float(last[0].item())
+    res["scan_consistent_with_reduce"] = bool(
+        abs(res["scan_last_plus_input"] - res["reduce_value"]) <= 1e-4 * abs(res["reduce_value"]))
     return res
 
 

@@ -75,6 +75,9 @@ def lib():
         L.b200_reduce_dot.argtypes = [vp, i, vp, vp, u64, vp]
         L.b200_block_prefix_reduce.argtypes = [vp, i, i, u64, u64, i, i, vp, vp]
         L.b200_prefix_reduce_carry.argtypes = [vp, i, i, u64, i, i, vp, vp, vp, vp]
+        L.b200_prefix_reduce_seeded.argtypes = [vp, i, i, u64, i, i, vp, vp, vp]
+        L.b200_scan_tile_elems.argtypes = [i]
+        L.b200_scan_tile_elems.restype = u32
         L.b200_compress.argtypes = [vp, vp, u64, vp, ctypes.POINTER(u32)]
         L.b200_compress_async.argtypes = [vp, vp, u64, vp, vp]
         L.b200_block_mkperm.argtypes = [vp, vp, u32, u32, u32, vp, vp, ctypes.POINTER(u32)]
@@ -234,6 +237,18 @@ def prefix_reduce_carry(vt, op, size, exclusive, reverse, in_, out, carry_in=Non
                                           int(bool(exclusive)), int(bool(reverse)),
                                           _ptr(in_), _ptr(out), _ptr(carry_in),
                                           _ptr(carry_out)))
+
+
+def scan_tile_elems(vt):
+    """Elements per tile of the streaming scan kernels (32 KiB)."""
+    return lib().b200_scan_tile_elems(vt)
+
+
+def prefix_reduce_seeded(vt, op, size, exclusive, reverse, in_, out, tile_seeds, stream=None):
+    """Whole-array prefix reduction with caller-supplied exclusive tile prefixes."""
+    _check(lib().b200_prefix_reduce_seeded(_stream(stream), vt, op, size, int(bool(exclusive)),
+                                           int(bool(reverse)), _ptr(in_), _ptr(out),
+                                           _ptr(tile_seeds)))
 
 
 def jit_compress(backend, in_, size, out, stream=None):

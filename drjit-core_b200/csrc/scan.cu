@@ -478,4 +478,37 @@ int b200_prefix_reduce_carry(void *stream_, int vt, int op, uint64_t size, int e
     return fn(call);
 }
 
+uint32_t b200_scan_tile_elems(int vt) {
+    const uint32_t tsize = type_size(vt);
+    return tsize ? 32768u / tsize : 0u; // DefaultGeom of scan_fast.cu: 512 threads x 4 x 16 bytes
+}
+
+int b200_prefix_reduce_seeded(void *stream_, int vt, int op, uint64_t size, int exclusive,
+                              int reverse, const void *in, void *out, const void *tile_seeds) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    const uint32_t tsize = type_size(vt);
+    if (!pick_scan(vt, op) || tsize == 0 || vt == B200_VT_FLOAT16)
+        return fail(B200_ERR_UNSUPPORTED,
+                    "b200_prefix_reduce_seeded(): no existing kernel for type=%s, op=%s!",
+                    type_name(vt), op_name(op));
+    if (size == 0)
+        return B200_OK;
+    if (!tile_seeds)
+        return fail(B200_ERR_INVALID, "b200_prefix_reduce_seeded(): tile_seeds is NULL!");
+    ScanCall call{ resolve_stream(stream_), in, out, size, size, exclusive != 0, reverse != 0,
+                   nullptr, nullptr, true };
+    call.seeds = tile_seeds;
+    bool handled = false;
+    rc = scan_fast_dispatch(vt, op, call, &handled);
+    if (rc)
+        return rc;
+    if (!handled)
+        return fail(B200_ERR_UNSUPPORTED,
+                    "b200_prefix_reduce_seeded(): needs 16-byte aligned arrays of fewer than 2^32 - 2^14 "
+                    "elements (use b200_prefix_reduce_carry otherwise)");
+    return B200_OK;
+}
+
 } // extern "C"

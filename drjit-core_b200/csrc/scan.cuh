@@ -17,6 +17,7 @@ struct ScanCall {
     const void *carry_in;
     void *carry_out;
     bool carry_api;    // whole array is one segment, optional carry
+    const void *seeds = nullptr; // carry_api only: exclusive prefix of every 32 KiB tile (no look-back)
 };
 
 /// Tries the streaming kernels (power-of-two blocks up to a tile; whole-array

@@ -62,6 +62,7 @@ struct FastParams {
     uint32_t *ticket;    // tile ticket counter (zero-initialised)
     const void *carry_in;
     void *carry_out;
+    const void *seeds;   // CHAIN: exclusive prefix per PHYSICAL tile, replaces the look-back
 };
 
 #if defined(B200_SCAN_TUNING)
@@ -289,6 +290,14 @@ scan_stream_kernel(const FastParams p) {
                     continue;
                 }
                 (void) c1;
+                if (p.seeds) { // prefixes are supplied: nothing to reduce or publish
+                    if (lane == 0) {
+                        s_mtile[m] = tile;
+                        mbar_arrive(&s_agg[m]);
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 const uint32_t ptile = p.reverse ? p.ntiles - 1 - tile : tile;
                 const uint64_t base = (uint64_t) ptile * TILE;
                 const uint4 *slot_ptr = slots + (size_t) slot * VECS;
@@ -371,7 +380,11 @@ scan_stream_kernel(const FastParams p) {
                 const V total = s_total[m];
                 const bool first = ((tile + p.tile_off) & p.seg_mask) == 0;
                 V P = R::identity();
-                if (first) {
+                if (p.seeds) {
+                    // SEEDED: the caller knows every tile's exclusive prefix (tile sums
+                    // from a reduce pass it had to make anyway) -- no chain, no polling
+                    P = ((const V *) p.seeds)[p.reverse ? p.ntiles - 1 - tile : tile];
+                } else if (first) {
                     if (p.carry_in)
                         P = *(const V *) p.carry_in;
                 } else {
@@ -416,7 +429,7 @@ scan_stream_kernel(const FastParams p) {
                 }
                 if (lane == 0) {
                     s_prefix[m] = P;
-                    if (p.carry_out && tile == p.ntiles - 1)
+                    if (p.carry_out && !p.seeds && tile == p.ntiles - 1)
                         *(V *) p.carry_out = R::apply(P, total);
                     mbar_arrive(&s_pref[m]);
                     DBG_ADD(2, DBG_CLOCK() - c1);
@@ -655,6 +668,7 @@ template <typename T, int Op, typename G> static int launch_fast_g(const ScanCal
     p.reverse = c.reverse;
     p.carry_in = c.carry_in;
     p.carry_out = c.carry_out;
+    p.seeds = c.seeds;
     {
         static int dbg = -1;
         if (dbg < 0) {

@@ -148,6 +148,18 @@ B200_API int b200_prefix_reduce_carry(void *stream, int vt, int op, uint64_t siz
                                       int exclusive, int reverse, const void *in,
                                       void *out, const void *carry_in, void *carry_out);
 
+/* Whole-array prefix reduction whose TILE prefixes are supplied by the caller:
+ * tile_seeds[t] (device, value type) = reduction of everything in front of tile t
+ * (behind it when reverse), tiles of b200_scan_tile_elems(vt) elements counted from
+ * the start of the array.  No look-back chain: every tile is independent, which
+ * is what the sharded front end wants -- it reduces its shard once anyway (for the
+ * exchange of the rank totals) and gets the tile sums from that pass.  New entry
+ * point (the reference has no counterpart).  Requires 16-byte aligned arrays. */
+B200_API uint32_t b200_scan_tile_elems(int vt);
+B200_API int b200_prefix_reduce_seeded(void *stream, int vt, int op, uint64_t size, int exclusive,
+                                       int reverse, const void *in, void *out,
+                                       const void *tile_seeds);
+
 /* ---------------------------------------------------------------- compress */
 
 /* jit_compress (jit.h:2387) = CUDAThreadState::compress

@@ -157,6 +157,45 @@ def test_prefix_carry_api(dr, O):
     assert not bad, bad
 
 
+def test_prefix_seeded_api(dr, O):
+    # b200_prefix_reduce_seeded: the caller supplies the exclusive prefix of every
+    # 32 KiB tile (what the sharded front end derives from its reduce pass); the
+    # result must equal the whole-array scan with a carry -- bit-exact for integers
+    bad = []
+    for tname, dt in (("u32", np.uint32), ("u64", np.uint64), ("f32", np.float32)):
+        tile = dr.scan_tile_elems(VT[tname])
+        assert tile * np.dtype(dt).itemsize == 32768
+        for size in (1, tile - 1, tile, 5 * tile + 17, (1 << 22) + 12345):
+            x = {"u32": u32_input, "u64": u64_input, "f32": f32_input}[tname](size)
+            ntiles = -(-size // tile)
+            pad = np.zeros(ntiles * tile, dtype=dt)
+            pad[:size] = x
+            tsums = pad.reshape(ntiles, tile).sum(axis=1, dtype=np.float64 if tname == "f32" else dt)
+            carry = dt(12345)
+            for excl, rev in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                if rev:
+                    seeds = (np.cumsum(tsums[::-1])[::-1] - tsums + carry).astype(dt)
+                else:
+                    seeds = (np.cumsum(tsums) - tsums + carry).astype(dt)
+                d_out = empty_dev(size, dt)
+                dr.prefix_reduce_seeded(VT[tname], OP["add"], size, excl, rev, to_dev(x), d_out, to_dev(seeds))
+                got = to_host(d_out, dt)
+                if tname == "f32":
+                    x64 = x.astype(np.float64)
+                    inc = np.cumsum(x64[::-1])[::-1] if rev else np.cumsum(x64)
+                    ref = inc - (x64 if excl else 0) + float(carry)
+                    if np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) > 1e-5:  # fp32 Add: 1e-5
+                        bad.append((tname, size, excl, rev))
+                else:
+                    ref = (O.block_prefix_reduce(VT[tname], OP["add"], x, size, excl, rev) + carry).astype(dt)
+                    if not np.array_equal(got, ref):
+                        bad.append((tname, size, excl, rev))
+    assert not bad, bad
+    with pytest.raises(RuntimeError):  # misaligned arrays are not served by the seeded kernel
+        dr.prefix_reduce_seeded(VT["u32"], OP["add"], 100000, 0, 0, to_dev(u32_input(100000), 1),
+                                empty_dev(100000, np.uint32, 1), to_dev(np.zeros(16, dtype=np.uint32)))
+
+
 def test_full_size_scan(dr, O):
     # 2^28 u32 exclusive prefix sum (BASELINE.json configs[0]), bit-exact
     n = 1 << 28

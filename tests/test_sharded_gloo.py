@@ -46,6 +46,23 @@ class OracleLocalOps:
         r = self.O.block_prefix_reduce(vt, op, ext, ext.size, exclusive, reverse)
         self._view(out, vt, size)[:] = r[:-1] if reverse else r[1:]
 
+    TILE = 16  # stand-in tile size of the seeded scan
+
+    def scan_tile_elems(self, vt, in_, out):
+        return self.TILE
+
+    def prefix_reduce_seeded(self, vt, op, size, exclusive, reverse, in_, out, seeds):
+        x = self._view(in_, vt, size)
+        sd = self._view(seeds, vt, -(-size // self.TILE))
+        res = np.empty_like(x)
+        for t in range(sd.size):
+            lo, hi = t * self.TILE, min(size, (t + 1) * self.TILE)
+            c = sd[t:t + 1]
+            ext = np.concatenate([x[lo:hi], c]) if reverse else np.concatenate([c, x[lo:hi]])
+            r = self.O.block_prefix_reduce(vt, op, ext, ext.size, exclusive, reverse)
+            res[lo:hi] = r[:-1] if reverse else r[1:]
+        self._view(out, vt, size)[:] = res
+
     def histogram(self, values, size, bucket_count, hist):
         k = values.numpy().view(np.uint32)[:size]
         hist.copy_(torch.from_numpy(np.bincount(k, minlength=bucket_count).astype(np.int32)))
@@ -66,6 +83,9 @@ def _worker(rank, world, port, results):
         VT, OP = oracle.VT, oracle.OP
         O = oracle.Oracle()
         sh = Sharded(device=torch.device("cpu"), local_ops=OracleLocalOps())
+        # a second front end that takes the tile-seeded scan path for every shard
+        sh_seeded = Sharded(device=torch.device("cpu"), local_ops=OracleLocalOps(), seeded_min_tiles=1)
+        sh.seeded_min_tiles = 1 << 30
         ok = True
         for total in (1, 2, 7, 1000, 100003):
             start, n = shard_bounds(total, world, rank)
@@ -79,10 +99,11 @@ def _worker(rank, world, port, results):
             # scan: rank's shard of the global result
             for excl in (0, 1):
                 for rev in (0, 1):
-                    out = torch.zeros(max(n, 1) * 4, dtype=torch.uint8)
-                    sh.prefix_reduce(VT["u32"], OP["add"], mine, n, excl, rev, out)
                     ref = O.block_prefix_reduce(VT["u32"], OP["add"], x, total, excl, rev)
-                    ok &= np.array_equal(out.numpy().view(np.uint32)[:n], ref[start:start + n])
+                    for front in (sh, sh_seeded):
+                        out = torch.zeros(max(n, 1) * 4, dtype=torch.uint8)
+                        front.prefix_reduce(VT["u32"], OP["add"], mine, n, excl, rev, out)
+                        ok &= np.array_equal(out.numpy().view(np.uint32)[:n], ref[start:start + n])
             # histogram: global counts and the rank's offsets
             k = key_input(total, 37)
             mine_k = torch.from_numpy(k[start:start + n].copy().view(np.uint8))
