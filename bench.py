@@ -174,7 +174,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args.log2n, 1),
+        "config": workload_config(args.log2n, args.gpus),
         "cpu_baseline": {"value": value, "unit": "elements/s", "cores": arm.cores,
                          "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0,

