@@ -111,3 +111,19 @@ def test_reduce_identity_table(lib):
     for vt in (4, 7, 8, 9, 10, 13, 14, 15):
         for op in range(1, 7):
             assert lib.b200_reduce_identity(vt, op) == O.reduce_identity(vt, op)
+
+
+def test_reference_header_client_links_against_this_library_only():
+    """tests/cpp/jit_h_client.cpp compiled against the REFERENCE's own jit.h
+    (oracle/Makefile, target tier3; built where /root/reference exists): every jit_*
+    symbol it needs must be one this library exports, under the same mangled name."""
+    client = os.path.join(ROOT, "oracle", "_ref", "jit_h_client_refhdr")
+    if not os.path.exists(client):
+        pytest.skip("oracle/_ref/jit_h_client_refhdr not built")
+    out = subprocess.run(["nm", "-u", client], capture_output=True, text=True, check=True).stdout
+    needed = {line.split()[-1].split("@")[0] for line in out.splitlines() if "jit_" in line}
+    assert len(needed) >= 12, needed
+    missing = needed - exported()
+    assert not missing, f"needed by a caller of the reference's jit.h but not exported: {sorted(missing)}"
+    ldd = subprocess.run(["ldd", client], capture_output=True, text=True).stdout
+    assert "libdrjit_core_b200.so" in ldd and "libref" not in ldd and "libdrjit-core" not in ldd
