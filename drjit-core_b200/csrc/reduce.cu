@@ -98,6 +98,35 @@ B200_DEVICE void rows_in_vector(typename ValueOf<T>::type *e, T *out, uint64_t q
 ///   (b) a block spans 2..32 adjacent lanes: butterfly over those lanes;
 ///   (c) a block spans 2..U whole rows: in-register tree over the lane's row
 ///       partials, then a full-warp butterfly.
+/// Full-warp reduction of C values per lane at once (C a power of two): at every
+/// level the lanes with 'BIT' set keep the upper half of the values and send the
+/// lower half to their partner (and vice versa), so C values cost C - 1 + log2(32 / C)
+/// shuffles instead of 5 C.  Returns, in every lane, the reduction of value
+/// j = lane >> (5 - log2 C) over all 32 lanes.  (A butterfly per value made the
+/// 512-byte blocks the slowest block size: 40 shuffles per 4 KiB.)
+template <typename V, int Op, int C, int BIT = 16>
+B200_DEVICE V warp_fold(V (&r)[C], uint32_t lane) {
+    using R = Red<V, Op>;
+    if constexpr (C == 1) {
+        V x = r[0];
+        #pragma unroll
+        for (int d = BIT; d > 0; d >>= 1)
+            x = R::apply(x, shfl_xor(x, d));
+        return x;
+    } else {
+        constexpr int H = C / 2;
+        V a[H];
+        const bool up = (lane & BIT) != 0;
+        #pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const V send = up ? r[i] : r[i + H];
+            const V keep = up ? r[i + H] : r[i];
+            a[i] = R::apply(keep, shfl_xor(send, BIT));
+        }
+        return warp_fold<V, Op, H, BIT / 2>(a, lane);
+    }
+}
+
 template <typename T, int Op, int U>
 __global__ void __launch_bounds__(REDUCE_THREADS, sizeof(T) >= 4 ? 4 : 2)
 reduce_rows_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size,
@@ -158,6 +187,13 @@ reduce_rows_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size,
         if (log2_bs <= LOG2_N + 5) { // (b)
             const uint32_t shift = log2_bs - LOG2_N; // log2(lanes per block), 1..5
             const int lanes = 1 << shift;
+            if (shift == 5) { // one block per row: the U rows are reduced together
+                const V x = warp_fold<V, Op, U>(r, lane);
+                const uint64_t o = row0 + (lane >> (5 - LOG2_U));
+                if ((lane & ((32 >> LOG2_U) - 1)) == 0 && o < nblocks)
+                    out[o] = from_value<T>(x);
+                continue;
+            }
             #pragma unroll
             for (int u = 0; u < U; ++u) {
                 uint64_t q = (row0 + u) * 32 + lane;
@@ -175,14 +211,24 @@ reduce_rows_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size,
                         r[u] = R::apply(r[u], r[u + (1 << s)]);
                 }
             }
-            #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if ((u & ((1 << log2_rows) - 1)) == 0) {
-                    V x = warp_reduce<V, Op>(r[u]);
-                    uint64_t o = (row0 + u) >> log2_rows;
-                    if (lane == 0 && o < nblocks)
-                        out[o] = from_value<T>(x);
-                }
+            // the U >> log2_rows remaining values are reduced over the warp together
+            auto finish = [&](auto tag) {
+                constexpr int C = decltype(tag)::value;
+                constexpr int LOG2_C = C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : 3;
+                V v[C];
+                #pragma unroll
+                for (int i = 0; i < C; ++i)
+                    v[i] = r[i * (U / C)];
+                const V x = warp_fold<V, Op, C>(v, lane);
+                const uint64_t o = (row0 >> log2_rows) + (lane >> (5 - LOG2_C));
+                if ((lane & ((32 >> LOG2_C) - 1)) == 0 && o < nblocks)
+                    out[o] = from_value<T>(x);
+            };
+            switch (U >> log2_rows) {
+                case 1: finish(std::integral_constant<int, 1>()); break;
+                case 2: if constexpr (U >= 2) finish(std::integral_constant<int, 2>()); break;
+                case 4: if constexpr (U >= 4) finish(std::integral_constant<int, 4>()); break;
+                default: break; // log2_rows >= 1: at most U / 2 values
             }
         }
     }
