@@ -187,10 +187,19 @@ reduce_rows_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size,
         if (log2_bs <= LOG2_N + 5) { // (b)
             const uint32_t shift = log2_bs - LOG2_N; // log2(lanes per block), 1..5
             const int lanes = 1 << shift;
-            if (shift == 5) { // one block per row: the U rows are reduced together
-                const V x = warp_fold<V, Op, U>(r, lane);
-                const uint64_t o = row0 + (lane >> (5 - LOG2_U));
-                if ((lane & ((32 >> LOG2_U) - 1)) == 0 && o < nblocks)
+            if (shift >= 3 && U == 8) {
+                // 8 .. 32 lanes per block: the U rows are reduced together, folding over
+                // the top three lane bits of a block; lane gets row (lane >> (shift - 3)) & 7
+                V x;
+                if (shift == 5)
+                    x = warp_fold<V, Op, U, 16>(r, lane);
+                else if (shift == 4)
+                    x = warp_fold<V, Op, U, 8>(r, lane);
+                else
+                    x = warp_fold<V, Op, U, 4>(r, lane);
+                const uint32_t j = (lane >> (shift - 3)) & 7u;
+                const uint64_t o = ((row0 + j) << (5 - shift)) + (lane >> shift);
+                if ((lane & ((1u << (shift - 3)) - 1u)) == 0 && o < nblocks)
                     out[o] = from_value<T>(x);
                 continue;
             }
