@@ -373,6 +373,133 @@ scatter_inc_kernel(uint32_t *__restrict__ target, const uint32_t *__restrict__ i
     }
 }
 
+/// Four consecutive entries per thread (128-bit loads / stores; 16-byte aligned
+/// index and out arrays).  A thread whose active entries all name one counter
+/// takes part as ONE unit with a count of up to four: the CTA-wide path then
+/// issues one atomic per 1024 entries (one shared counter: 0.44 -> 0.16 ms for
+/// 2^26 entries), the warp path one per run of neighbouring threads with the
+/// same counter.  Warps in which some thread names several counters issue one
+/// atomic per entry.
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_inc_vec4_kernel(uint32_t *__restrict__ target, const uint32_t *__restrict__ index,
+                        const uint8_t *__restrict__ mask, uint32_t *__restrict__ out, uint64_t nvec) {
+    constexpr int WARPS = SCATTER_THREADS / 32;
+    __shared__ uint32_t s_idx[WARPS], s_cnt[WARPS], s_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
+    for (uint64_t cbase = (uint64_t) blockIdx.x * SCATTER_THREADS; cbase < nvec; cbase += stride) {
+        const uint64_t q = cbase + threadIdx.x;
+        const bool in_range = q < nvec;
+        uint32_t idx[4] = { 0, 0, 0, 0 };
+        bool on[4] = { false, false, false, false };
+        if (in_range) {
+            const uint4 i4 = ld_stream(index + 4 * q);
+            idx[0] = i4.x; idx[1] = i4.y; idx[2] = i4.z; idx[3] = i4.w;
+            uint32_t m4 = 0x01010101u;
+            if (mask)
+                m4 = __ldcs((const uint32_t *) (mask + 4 * q));
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                on[k] = ((m4 >> (8 * k)) & 0xffu) != 0;
+        }
+        // the thread as a unit: number of active entries, their common counter (if any)
+        uint32_t t_cnt = 0, t_idx = 0;
+        bool t_uniform = true;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (on[k]) {
+                if (t_cnt == 0)
+                    t_idx = idx[k];
+                else
+                    t_uniform &= idx[k] == t_idx;
+                t_cnt++;
+            }
+        }
+        const uint32_t active = __ballot_sync(FULL_MASK, t_cnt != 0);
+        const bool units = __all_sync(FULL_MASK, t_uniform); // warp-uniform
+        const uint32_t lead = __ffs(active | 0x80000000u) - 1;
+        const uint32_t lead_idx = __shfl_sync(FULL_MASK, t_idx, lead);
+        const bool warp_uniform = units && __all_sync(FULL_MASK, t_cnt == 0 || t_idx == lead_idx);
+        // inclusive prefix of the unit counts over the lanes
+        uint32_t incl = t_cnt;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= (uint32_t) d)
+                incl += up;
+        }
+        const uint32_t warp_total = __shfl_sync(FULL_MASK, incl, 31);
+
+        if (lane == 0) {
+            s_cnt[warp] = warp_total;
+            s_idx[warp] = warp_uniform ? lead_idx : 0xffffffffu;
+        }
+        __syncthreads();
+        uint32_t total = 0, before = 0, ref = 0xffffffffu;
+        bool cta_uniform = true;
+        #pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s_cnt[w], x = s_idx[w];
+            if (c) {
+                if (ref == 0xffffffffu)
+                    ref = x;
+                cta_uniform &= x == ref && x != 0xffffffffu;
+            }
+            total += c;
+            before += (uint32_t) w < warp ? c : 0u;
+        }
+
+        uint32_t old[4] = { 0, 0, 0, 0 };
+        if (cta_uniform && total) {
+            if (threadIdx.x == 0)
+                s_base = atomicAdd(target + ref, total);
+            __syncthreads();
+            uint32_t o = s_base + before + incl - t_cnt;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (on[k])
+                    old[k] = o++;
+        } else if (units) {
+            if (active) {
+                // runs of neighbouring threads with the same counter
+                const uint32_t prev_idx = __shfl_up_sync(FULL_MASK, t_idx, 1);
+                const bool head = lane == 0 || t_cnt == 0 || !((active >> (lane - 1)) & 1u) || t_idx != prev_idx;
+                const uint32_t heads = __ballot_sync(FULL_MASK, head);
+                const uint32_t my_head = 31u - __clz(heads & (lt | (1u << lane)));
+                const uint32_t above = heads & ~((2u << lane) - 1u);
+                const uint32_t last = above ? (uint32_t) __ffs(above) - 2u : 31u;
+                // entries in this lane's run: inclusive prefix at its end minus exclusive at its start
+                const uint32_t head_excl = __shfl_sync(FULL_MASK, incl - t_cnt, my_head);
+                const uint32_t last_incl = __shfl_sync(FULL_MASK, incl, last);
+                uint32_t prev = 0;
+                if (head && t_cnt)
+                    prev = atomicAdd(target + t_idx, last_incl - head_excl);
+                prev = __shfl_sync(FULL_MASK, prev, my_head);
+                uint32_t o = prev + (incl - t_cnt) - head_excl;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (on[k])
+                        old[k] = o++;
+            }
+        } else {
+            // some thread names several counters (incoherent indices): one atomic per
+            // entry, all four of a thread in flight together
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (on[k])
+                    old[k] = atomicAdd(target + idx[k], 1u);
+        }
+        if (in_range) {
+            uint4 o4;
+            o4.x = on[0] ? old[0] : 0u; o4.y = on[1] ? old[1] : 0u;
+            o4.z = on[2] ? old[2] : 0u; o4.w = on[3] ? old[3] : 0u;
+            st_stream(out + 4 * q, o4);
+        }
+        __syncthreads(); // s_idx / s_cnt / s_base are rewritten in the next step
+    }
+}
+
 // -------------------------------------------------------------- packet scatter
 //
 // jit_var_scatter_packet with a reduction (jit.h:1117; emitter
@@ -767,6 +894,22 @@ int b200_scatter_inc(void *stream_, uint32_t *target, const uint32_t *index, con
     if (n == 0)
         return B200_OK;
     cudaStream_t stream = resolve_stream(stream_);
+    if (n >= 4096 && ((uintptr_t) index % 16) == 0 && ((uintptr_t) out % 16) == 0 &&
+        (!mask || ((uintptr_t) mask % 4) == 0)) {
+        // four entries per thread; the (< 4) tail entries go through the scalar kernel
+        const uint64_t nvec = n / 4;
+        uint32_t vgrid = (uint32_t) std::max<uint64_t>(
+            1, std::min<uint64_t>(ceil_div(nvec, (uint64_t) SCATTER_THREADS), (uint64_t) sm_count() * 8));
+        scatter_inc_vec4_kernel<<<vgrid, SCATTER_THREADS, 0, stream>>>(target, index, mask, out, nvec);
+        B200_LAUNCH_CHECK();
+        if (n % 4 == 0)
+            return B200_OK;
+        index += 4 * nvec;
+        out += 4 * nvec;
+        if (mask)
+            mask += 4 * nvec;
+        n %= 4;
+    }
     uint32_t grid = (uint32_t) std::max<uint64_t>(
         1, std::min<uint64_t>(ceil_div(n, (uint64_t) SCATTER_THREADS), (uint64_t) sm_count() * 16));
     scatter_inc_kernel<<<grid, SCATTER_THREADS, 0, stream>>>(target, index, mask, out, n);
