@@ -127,3 +127,21 @@ def test_reference_header_client_links_against_this_library_only():
     assert not missing, f"needed by a caller of the reference's jit.h but not exported: {sorted(missing)}"
     ldd = subprocess.run(["ldd", client], capture_output=True, text=True).stdout
     assert "libdrjit_core_b200.so" in ldd and "libref" not in ldd and "libdrjit-core" not in ldd
+
+
+def test_tier3_library_needs_only_exported_b200_symbols():
+    """oracle/_ref/libref_cuda_b200.so = the unmodified reference objects + the
+    CUDAThreadState adapter (oracle/tier3_adapter.cpp): every b200_* symbol it imports
+    must be exported by this library, and the reference's test programs must resolve
+    both libraries (so that the GPU run cannot silently skip them)."""
+    lib3 = os.path.join(ROOT, "oracle", "_ref", "libref_cuda_b200.so")
+    if not os.path.exists(lib3):
+        pytest.skip("oracle/_ref/libref_cuda_b200.so not built (make -C oracle tier3)")
+    out = subprocess.run(["nm", "-D", "-u", lib3], capture_output=True, text=True, check=True).stdout
+    needed = {line.split()[-1].split("@")[0] for line in out.splitlines() if " b200_" in line}
+    assert {"b200_block_reduce", "b200_block_prefix_reduce", "b200_reduce_dot", "b200_compress",
+            "b200_block_mkperm", "b200_memset_async"} <= needed
+    assert not (needed - exported())
+    prog = os.path.join(ROOT, "oracle", "_ref", "test_reductions_b200")
+    ldd = subprocess.run(["ldd", prog], capture_output=True, text=True).stdout
+    assert "libref_cuda_b200.so" in ldd and "libdrjit_core_b200.so" in ldd and "not found" not in ldd
