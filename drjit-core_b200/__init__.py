@@ -36,6 +36,20 @@ class ReduceMode:
     Auto, Direct, Local, NoConflicts, Expand, Permute = range(6)
 
 
+class JitFlag:  # jit.h:1734-1742 (the bits this path honours)
+    KernelHistory, LaunchBlocking, ForbidSynchronization = 1 << 15, 1 << 16, 1 << 17
+
+
+class KernelType:  # jit.h:2597-2634
+    (JIT, BlockReduce, BlockPrefixReduce, Dot, BatchedGemm, Compress, MkPerm, Memcpy, Memset,
+     Poke, Aggregate, LLVMHostFunc) = range(12)
+
+
+class KernelRecord(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int), ("size", ctypes.c_uint64),
+                ("execution_time_ms", ctypes.c_float)]
+
+
 TYPE_SIZE = (0, 1, 0, 1, 1, 2, 2, 4, 4, 8, 8, 8, 0, 2, 4, 8)  # src/var.cpp:117-119
 
 
@@ -63,6 +77,17 @@ def lib():
         L.b200_malloc.restype = ctypes.c_void_p
         L.b200_malloc.argtypes = [ctypes.c_size_t, ctypes.c_int]
         L.b200_free.argtypes = [ctypes.c_void_p]
+        L.b200_free_on.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.b200_malloc_migrate.restype = ctypes.c_void_p
+        L.b200_malloc_migrate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.b200_sync_stream.argtypes = [ctypes.c_void_p]
+        L.b200_set_flags.argtypes = [ctypes.c_uint32]
+        L.b200_set_flags.restype = None
+        L.b200_flags.restype = ctypes.c_uint32
+        L.b200_set_flag.argtypes = [ctypes.c_uint32, ctypes.c_int]
+        L.b200_set_flag.restype = None
+        L.b200_kernel_history.argtypes = [ctypes.POINTER(KernelRecord), ctypes.c_int]
+        L.b200_kernel_history_clear.restype = None
         L.b200_reduce_identity.restype = ctypes.c_uint64
         L.b200_launch_count.restype = ctypes.c_uint64
         vp, u64, u32, i = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
@@ -81,6 +106,7 @@ def lib():
         L.b200_compress.argtypes = [vp, vp, u64, vp, ctypes.POINTER(u32)]
         L.b200_compress_async.argtypes = [vp, vp, u64, vp, vp]
         L.b200_block_mkperm.argtypes = [vp, vp, u32, u32, u32, vp, vp, ctypes.POINTER(u32)]
+        L.b200_block_mkperm_async.argtypes = [vp, vp, u32, u32, u32, vp, vp]
         L.b200_mkperm_histogram.argtypes = [vp, vp, u64, u32, vp]
         L.b200_scatter_reduce.argtypes = [vp, i, i, i, vp, vp, vp, vp, u64]
         L.b200_scatter_inc.argtypes = [vp, vp, vp, vp, vp, u64]
@@ -170,8 +196,54 @@ def jit_malloc(backend, size, shared=0):
     return ptr
 
 
-def jit_free(ptr):
-    _check(lib().b200_free(ptr))
+def jit_free(ptr, stream=None):
+    """Released in the order of the stream the binding launches on (torch's current
+    stream when torch is up) -- the stream that last used the block."""
+    s = _stream(stream)
+    _check(lib().b200_free_on(s, ptr) if s else lib().b200_free(ptr))
+
+
+def jit_malloc_migrate(ptr, backend, move=1):
+    """jit.h:516: JitBackend.CUDA -> device memory, JitBackend.None_ -> pinned host."""
+    if backend not in (JitBackend.CUDA, JitBackend.None_):
+        _require_cuda(backend, "jit_malloc_migrate")
+    r = lib().b200_malloc_migrate(ptr, 0 if backend == JitBackend.CUDA else 1, int(bool(move)))
+    if not r:
+        _check(1)
+    return r
+
+
+def jit_cuda_sync_stream(stream):
+    """jit.h:243-255: `stream` (handle) waits for the work enqueued on the library stream."""
+    _check(lib().b200_sync_stream(stream))
+
+
+def jit_set_flags(flags):
+    lib().b200_set_flags(flags)
+
+
+def jit_flags():
+    return int(lib().b200_flags())
+
+
+def jit_set_flag(flag, enable):
+    lib().b200_set_flag(flag, int(bool(enable)))
+
+
+def jit_flag(flag):
+    return bool(jit_flags() & flag)
+
+
+def jit_kernel_history():
+    """[(KernelType, size, execution_time_ms)] of the primitive calls recorded while
+    JitFlag.KernelHistory was set; clears the history (jit.h:2715-2737)."""
+    buf = (KernelRecord * 4096)()
+    n = min(lib().b200_kernel_history(buf, 4096), 4096)
+    return [(buf[i].type, int(buf[i].size), float(buf[i].execution_time_ms)) for i in range(n)]
+
+
+def jit_kernel_history_clear():
+    lib().b200_kernel_history_clear()
 
 
 def jit_memcpy(backend, dst, src, size):
@@ -275,6 +347,12 @@ def jit_block_mkperm(backend, values, size, block_size, bucket_count, perm, offs
                                    bucket_count, _ptr(perm), _ptr(offsets),
                                    ctypes.byref(unique)))
     return unique.value
+
+
+def block_mkperm_async(values, size, block_size, bucket_count, perm, offsets, stream=None):
+    """Enqueue only; after a stream sync offsets[4 * bucket_count] is the unique count."""
+    _check(lib().b200_block_mkperm_async(_stream(stream), _ptr(values), size, block_size,
+                                         bucket_count, _ptr(perm), _ptr(offsets)))
 
 
 def mkperm_histogram(values, size, bucket_count, hist, stream=None):

@@ -32,6 +32,27 @@ int sm_count();
 void count_launch(uint64_t n = 1);
 /// Make sure the runtime is initialised (lazily calls b200_init)
 int ensure_init();
+/// Current JitFlag bits (b200_set_flags)
+uint32_t flags();
+/// B200_ERR_SYNC_FORBIDDEN (with the reference's message) when
+/// JitFlag::ForbidSynchronization is set, else B200_OK.  Called by every entry
+/// point that blocks on the stream (src/init.cpp:503-505).
+int sync_forbidden();
+
+/// JitFlag::KernelHistory: brackets one primitive call with two events on its
+/// stream and appends a record of the given KernelType (jit.h:2597-2634) -- what
+/// CUDAThreadState::submit does around every precompiled kernel of the reference
+/// (src/cuda_ts.cpp:23-46).  A no-op when the flag is clear.
+struct HistoryScope {
+    HistoryScope(cudaStream_t stream, int type, uint64_t size);
+    ~HistoryScope();
+    HistoryScope(const HistoryScope &) = delete;
+    HistoryScope &operator=(const HistoryScope &) = delete;
+    cudaStream_t stream;
+    int type;
+    uint64_t size;
+    void *start;
+};
 
 /// Stream-ordered temporary memory (CUDA memory-pool backed)
 void *temp_alloc(size_t bytes, cudaStream_t stream);

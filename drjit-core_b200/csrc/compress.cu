@@ -230,9 +230,12 @@ static constexpr uint32_t CT_STAGE = 2 * 512 + 4;                   // staging w
 static constexpr uint32_t CT_GROUP_SHIFT = 7;                       // 128 tiles per counter group
 static_assert((1u << CT_GROUP_SHIFT) <= CT_THREADS, "one tile count per thread");
 
-/// bit k of the result = bit 0 of byte k of w (k < 4)
+/// bit k of the result = (byte k of w != 0) (k < 4).  The same predicate as the
+/// single-pass kernel for small masks (any non-zero byte selects the entry), so
+/// that count and indices do not depend on which path serves a call; the
+/// reference defines only 0 / 1 (jit.h:2377-2379).
 B200_DEVICE uint32_t pack4(uint32_t w) {
-    return (((w & 0x01010101u) * 0x00204081u) >> 21) & 0xfu;
+    return ((((nonzero_bytes(w) >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xfu;
 }
 
 B200_DEVICE uint32_t pack16(uint4 v) {
@@ -539,6 +542,7 @@ int b200_compress_async(void *stream_, const uint8_t *in, uint64_t size, uint32_
     }
     if (size > 0xffffffffull)
         return fail(B200_ERR_INVALID, "jit_compress(): array too large (indices are 32 bit)!");
+    HistoryScope hs(stream, B200_KERNEL_COMPRESS, size);
     // small masks: one launch of the single-pass kernel; large ones: bit-packed tiles
     if (size > 32768)
         return compress_tiles(stream, in, size, out, count_dev);
@@ -569,6 +573,8 @@ int b200_compress(void *stream_, const uint8_t *in, uint64_t size, uint32_t *out
         *count = 0;
         return B200_OK;
     }
+    if ((rc = sync_forbidden())) // the reference calls jitc_sync_thread (src/cuda_ts.cpp:759)
+        return rc;
     cudaStream_t stream = resolve_stream(stream_);
     // the reference reads the count from pinned memory after a full stream
     // synchronisation (src/cuda_ts.cpp:759-762); here the kernel writes it there

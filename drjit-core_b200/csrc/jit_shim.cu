@@ -8,9 +8,14 @@
 #include "../../include/drjit_b200_jit.h"
 #include "../../include/drjit_b200.h"
 
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -60,6 +65,63 @@ void jit_sync_thread() {
     }
     if (stream)
         check(b200_sync(stream)); // lock not held while blocking (src/init.cpp:516-517)
+}
+
+void jit_cuda_sync_stream(uintptr_t stream) {
+    std::lock_guard<std::recursive_mutex> guard(g_api_lock);
+    check(b200_sync_stream((void *) stream));
+}
+
+void jit_set_flags(uint32_t flags) { b200_set_flags(flags); }
+uint32_t jit_flags() { return b200_flags(); }
+void jit_set_flag(JitFlag flag, int enable) { b200_set_flag((uint32_t) flag, enable); }
+int jit_flag(JitFlag flag) { return (b200_flags() & (uint32_t) flag) ? 1 : 0; }
+
+KernelHistoryEntry *jit_kernel_history() {
+    // src/init.cpp jitc_kernel_history: waits for the events, returns a malloc'ed array
+    // terminated by an entry whose backend is None; NULL when the history is empty
+    std::lock_guard<std::recursive_mutex> guard(g_api_lock);
+    std::vector<B200KernelRecord> recs(64);
+    int n = b200_kernel_history(recs.data(), (int) recs.size());
+    // (records beyond the capacity are dropped by the C-ABI call; ask generously)
+    if (n > (int) recs.size())
+        n = (int) recs.size();
+    if (n == 0)
+        return nullptr;
+    KernelHistoryEntry *out = (KernelHistoryEntry *) calloc((size_t) n + 1, sizeof(KernelHistoryEntry));
+    for (int i = 0; i < n; ++i) {
+        out[i].backend = JitBackend::CUDA;
+        out[i].type = (KernelType) recs[i].type;
+        out[i].recording_mode = KernelRecordingMode::Inactive;
+        out[i].size = (uint32_t) recs[i].size;
+        out[i].input_count = 1;
+        out[i].output_count = 1;
+        out[i].execution_time = recs[i].execution_time_ms;
+    }
+    return out;
+}
+
+void jit_kernel_history_clear() {
+    std::lock_guard<std::recursive_mutex> guard(g_api_lock);
+    b200_kernel_history_clear();
+}
+
+void *jit_malloc_migrate(void *ptr, JitBackend backend, int move) {
+    std::lock_guard<std::recursive_mutex> guard(g_api_lock);
+    if (!ptr)
+        return nullptr;
+    int kind;
+    if (backend == JitBackend::CUDA)
+        kind = 0;
+    else if (backend == JitBackend::None)
+        kind = 1; // host: pinned memory
+    else
+        throw std::runtime_error("jit_malloc_migrate(): this build only provides the CUDA backend "
+                                 "(no CPU fallback).");
+    void *r = b200_malloc_migrate(ptr, kind, move);
+    if (!r)
+        raise_last();
+    return r;
 }
 
 int jit_cuda_device_count() {
@@ -154,16 +216,31 @@ void jit_block_prefix_reduce(JitBackend backend, VarType type, ReduceOp op, uint
                                    reverse, in, out));
 }
 
+// The two synchronising primitives hold the API lock for the whole enqueue (temporary
+// allocations, per-device caches, launches) and drop it only while waiting for the
+// stream -- state.lock + unlock_guard of the reference (src/cuda_ts.cpp:759, :964-967).
+
 uint32_t jit_compress(JitBackend backend, const uint8_t *in, uint32_t size, uint32_t *out) {
     require_cuda(backend, "jit_compress");
-    uint32_t count = 0;
+    if (size == 0)
+        return 0;
+    if (b200_flags() & B200_FLAG_FORBID_SYNCHRONIZATION)
+        throw std::runtime_error("Attempted to synchronize in a context, where synchronization "
+                                 "was explicitly forbidden!");
+    // the count lands in pinned memory owned by this call
+    uint32_t *count_pinned = (uint32_t *) jit_malloc(JitBackend::CUDA, sizeof(uint32_t), 1);
     void *stream;
+    int rc;
     {
         std::lock_guard<std::recursive_mutex> guard(g_api_lock);
         stream = b200_stream();
+        rc = b200_compress_async(stream, in, size, out, count_pinned);
     }
-    // enqueue + blocking read-back; the API lock is not held while waiting
-    check(b200_compress(stream, in, size, out, &count));
+    if (rc == B200_OK)
+        rc = b200_sync(stream); // lock not held while blocking
+    uint32_t count = rc == B200_OK ? *count_pinned : 0;
+    jit_free(count_pinned);
+    check(rc);
     return count;
 }
 
@@ -171,13 +248,20 @@ uint32_t jit_block_mkperm(JitBackend backend, const uint32_t *values, uint32_t s
                           uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
                           uint32_t *offsets) {
     require_cuda(backend, "jit_block_mkperm");
-    uint32_t unique = 0;
+    if (size == 0)
+        return 0;
+    // (no ForbidSynchronization check: the reference waits on an event here without
+    // one, src/cuda_ts.cpp:964-967)
+    const bool waits = offsets && (block_size >= size);
     void *stream;
     {
         std::lock_guard<std::recursive_mutex> guard(g_api_lock);
         stream = b200_stream();
+        check(b200_block_mkperm_async(stream, values, size, block_size, bucket_count, perm, offsets));
     }
-    check(b200_block_mkperm(stream, values, size, block_size, bucket_count, perm, offsets,
-                            &unique));
-    return unique;
+    if (!waits)
+        return 0;
+    if (cudaStreamSynchronize((cudaStream_t) stream) != cudaSuccess) // lock not held while blocking
+        throw std::runtime_error("jit_block_mkperm(): stream synchronisation failed");
+    return offsets[4 * (size_t) bucket_count];
 }

@@ -31,7 +31,16 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace b200 {
+
+/// NVTX range (header-only NVTX v3: a no-op unless a profiler is attached) -- the
+/// reference brackets jit_block_mkperm with a ProfilerPhase (src/util.cpp:218-229)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static constexpr int MKPERM_WARPS = 16;
 static constexpr int MKPERM_THREADS = MKPERM_WARPS * 32;
@@ -1012,9 +1021,25 @@ int b200_mkperm_histogram(void *stream_, const uint32_t *values, uint64_t size,
     return histogram_launch(stream, values, size, bucket_count, hist);
 }
 
+static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
+                       uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
+                       uint32_t *offsets, uint32_t *unique, bool wait);
+
 int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
                       uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
                       uint32_t *offsets, uint32_t *unique) {
+    return mkperm_impl(stream_, values, size, block_size, bucket_count, perm, offsets, unique, true);
+}
+
+int b200_block_mkperm_async(void *stream_, const uint32_t *values, uint32_t size,
+                            uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
+                            uint32_t *offsets) {
+    return mkperm_impl(stream_, values, size, block_size, bucket_count, perm, offsets, nullptr, false);
+}
+
+static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
+                       uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
+                       uint32_t *offsets, uint32_t *unique, bool wait) {
     int rc = ensure_init();
     if (rc)
         return rc;
@@ -1030,9 +1055,15 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
     if (block_size > size)
         block_size = size;
 
+    const uint64_t ngroups = ceil_div(size, block_size);
+    // NOTE JitFlag::ForbidSynchronization: with offsets the call waits, but the
+    // reference waits on an EVENT (cuEventSynchronize, src/cuda_ts.cpp:964-967), not
+    // through jitc_sync_thread, so it does not raise under that flag -- neither does
+    // this entry point (jit_compress, jit_all / jit_any and jit_memcpy do).
     cudaStream_t stream = resolve_stream(stream_);
     const int sms = sm_count();
-    const uint64_t ngroups = ceil_div(size, block_size);
+    HistoryScope hs(stream, B200_KERNEL_MKPERM, size);
+    NvtxRange nvtx("jit_block_mkperm"); // ProfilerPhase of src/util.cpp:218-229
 
     // one sorting group (vectorised method dispatch) or groups of at least half a tile:
     // ranked tiles.  Smaller groups would leave the tiles mostly empty: row kernels.
@@ -1041,7 +1072,7 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
                            ngroups == 1 ? offsets : nullptr);
         if (rc)
             return rc;
-        if (offsets && ngroups == 1) {
+        if (wait && offsets && ngroups == 1) {
             // the reference waits on an event here (src/cuda_ts.cpp:964-967)
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
             if (unique)
@@ -1204,7 +1235,7 @@ int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
 
     cleanup();
 
-    if (offsets && ngroups == 1) {
+    if (wait && offsets && ngroups == 1) {
         // the reference waits on an event here (src/cuda_ts.cpp:964-967)
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
         if (unique)

@@ -682,6 +682,7 @@ int b200_block_reduce(void *stream_, int vt, int op, uint64_t size, uint64_t blo
     if (((uintptr_t) in % tsize) != 0 || ((uintptr_t) out % tsize) != 0)
         return fail(B200_ERR_INVALID, "jit_block_reduce(): misaligned pointer!");
     cudaStream_t stream = resolve_stream(stream_);
+    HistoryScope hs(stream, B200_KERNEL_BLOCK_REDUCE, size);
     if (block_size == 1) {
         B200_CUDA_CHECK(cudaMemcpyAsync(out, in, size * tsize, cudaMemcpyDeviceToDevice, stream));
         return B200_OK;
@@ -709,6 +710,7 @@ int b200_reduce_dot(void *stream_, int vt, const void *a, const void *b, uint64_
         B200_CUDA_CHECK(cudaMemsetAsync(out, 0, tsize, stream));
         return B200_OK;
     }
+    HistoryScope hs(stream, B200_KERNEL_DOT, size);
     switch (vt) {
         case B200_VT_FLOAT16: return launch_dot<__half>(stream, a, b, size, out);
         case B200_VT_FLOAT32: return launch_dot<float>(stream, a, b, size, out);
@@ -742,6 +744,8 @@ static int bool_reduce_sync(void *stream_, const uint8_t *values, uint64_t size,
                             int op) {
     int rc = b200::ensure_init();
     if (rc)
+        return rc;
+    if ((rc = b200::sync_forbidden())) // jitc_all / jitc_any wait for the stream (src/util.cpp:153-180)
         return rc;
     cudaStream_t stream = b200::resolve_stream(stream_);
     uint8_t *tmp = (uint8_t *) b200::temp_alloc(4, stream);

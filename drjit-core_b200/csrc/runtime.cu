@@ -28,11 +28,30 @@ struct DeviceState {
 };
 
 static std::mutex g_lock;
-static bool g_initialised = false;
+static std::atomic<bool> g_initialised{ false };
+// Sized once by b200_init() and only cleared by b200_shutdown() (under g_lock);
+// DeviceState::stream is published with release / acquire semantics.
 static std::vector<DeviceState> g_devices;
 static std::atomic<uint64_t> g_launches{ 0 };
-// pointer -> kind (0 device, 1 pinned host) for b200_free
-static std::unordered_map<void *, int> g_allocs;
+static std::atomic<uint32_t> g_flags{ 0 };
+// the stream the calling thread's current API call runs on (JitFlag::LaunchBlocking)
+static thread_local cudaStream_t tls_stream = nullptr;
+// pointer -> where it came from, for b200_free
+struct AllocInfo {
+    int kind;            // 0 device, 1 pinned host
+    int device;          // device that was current at allocation time
+    cudaStream_t stream; // stream the allocation was ordered on
+    size_t bytes;        // rounded size
+};
+static std::unordered_map<void *, AllocInfo> g_allocs;
+
+// ---- kernel history (JitFlag::KernelHistory, jit.h:2597-2709; src/cuda_ts.cpp:23-46)
+struct HistoryRecord {
+    int type;
+    uint64_t size;
+    cudaEvent_t start, end;
+};
+static std::vector<HistoryRecord> g_history; // g_lock
 
 int fail(int code, const char *fmt, ...) {
     char buf[1024];
@@ -51,7 +70,49 @@ int cuda_fail(cudaError_t err, const char *what) {
                 cudaGetErrorString(err), what);
 }
 
-void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch(uint64_t n) {
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    // JitFlag::LaunchBlocking: "force synchronization after every kernel launch"
+    // (jit.h:1736-1739; src/cuda_ts.cpp:37-38)
+    if (g_flags.load(std::memory_order_relaxed) & B200_FLAG_LAUNCH_BLOCKING)
+        cudaStreamSynchronize(tls_stream);
+}
+
+uint32_t flags() { return g_flags.load(std::memory_order_relaxed); }
+
+int sync_forbidden() {
+    // src/init.cpp:503-505
+    if (g_flags.load(std::memory_order_relaxed) & B200_FLAG_FORBID_SYNCHRONIZATION)
+        return fail(B200_ERR_SYNC_FORBIDDEN,
+                    "Attempted to synchronize in a context, where synchronization was "
+                    "explicitly forbidden!");
+    return B200_OK;
+}
+
+HistoryScope::HistoryScope(cudaStream_t stream_, int type_, uint64_t size_)
+    : stream(stream_), type(type_), size(size_), start(nullptr) {
+    if (!(g_flags.load(std::memory_order_relaxed) & B200_FLAG_KERNEL_HISTORY))
+        return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess || cudaEventRecord(ev, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    start = ev;
+}
+
+HistoryScope::~HistoryScope() {
+    if (!start)
+        return;
+    cudaEvent_t end;
+    if (cudaEventCreate(&end) != cudaSuccess || cudaEventRecord(end, stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaEventDestroy((cudaEvent_t) start);
+        return;
+    }
+    std::lock_guard<std::mutex> guard(g_lock);
+    g_history.push_back({ type, size, (cudaEvent_t) start, end });
+}
 
 const char *type_name(int vt) {
     // src/var.cpp type_name table
@@ -79,16 +140,16 @@ static int current_device() {
 }
 
 int ensure_init() {
-    if (g_initialised)
+    if (g_initialised.load(std::memory_order_acquire))
         return B200_OK;
     return b200_init();
 }
 
 static int prepare_device(int dev) {
-    DeviceState &d = g_devices[dev];
-    if (d.stream)
-        return B200_OK;
     std::lock_guard<std::mutex> guard(g_lock);
+    if (dev < 0 || dev >= (int) g_devices.size())
+        return fail(B200_ERR_INVALID, "b200: invalid device %d (library shut down?)", dev);
+    DeviceState &d = g_devices[dev];
     if (d.stream)
         return B200_OK;
     if (d.cc_major < 10)
@@ -97,24 +158,41 @@ static int prepare_device(int dev) {
                     "this library are built for sm_100a only",
                     dev, d.cc_major, d.cc_minor);
     B200_CUDA_CHECK(cudaSetDevice(dev));
-    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    // A BLOCKING stream, like the reference's (cuStreamCreate(.., CU_STREAM_DEFAULT),
+    // src/cuda_core.cpp:480): work on it is implicitly ordered with the legacy
+    // default stream, so callers that stage inputs with cudaMemset / cudaMemcpy / their
+    // own stream-0 kernels, or read results with cudaMemcpy right after a primitive,
+    // keep the ordering they get from the reference ("Dr.Jit implicitly synchronizes
+    // with respect to [the NULL stream]", jit.h:249-250).
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamDefault));
     return B200_OK;
 }
 
-cudaStream_t resolve_stream(void *stream) {
-    if (stream)
-        return (cudaStream_t) stream;
+static cudaStream_t library_stream() {
     int dev = current_device();
-    if (dev >= 0 && dev < (int) g_devices.size() && prepare_device(dev) == B200_OK)
-        return g_devices[dev].stream;
-    return nullptr;
+    if (prepare_device(dev) != B200_OK)
+        return nullptr;
+    std::lock_guard<std::mutex> guard(g_lock);
+    return dev < (int) g_devices.size() ? g_devices[dev].stream : nullptr;
+}
+
+cudaStream_t resolve_stream(void *stream) {
+    cudaStream_t s = stream ? (cudaStream_t) stream : library_stream();
+    tls_stream = s;
+    return s;
 }
 
 int sm_count() {
+    static thread_local int cached_dev = -1, cached = 148;
     int dev = current_device();
-    if (dev >= 0 && dev < (int) g_devices.size())
-        return g_devices[dev].sm_count;
-    return 148;
+    if (dev != cached_dev) {
+        std::lock_guard<std::mutex> guard(g_lock);
+        if (dev >= 0 && dev < (int) g_devices.size()) {
+            cached = g_devices[dev].sm_count;
+            cached_dev = dev;
+        }
+    }
+    return cached;
 }
 
 // Freed temporaries must stay cached in the device's default pool: with the
@@ -203,7 +281,7 @@ extern "C" {
 
 int b200_init(void) {
     std::lock_guard<std::mutex> guard(g_lock);
-    if (g_initialised)
+    if (g_initialised.load(std::memory_order_acquire))
         return B200_OK;
     int count = 0;
     cudaError_t err = cudaGetDeviceCount(&count);
@@ -227,7 +305,7 @@ int b200_init(void) {
         // that a rank of a multi-process job only ever touches its own GPU.
     }
     cudaSetDevice(prev);
-    g_initialised = true;
+    g_initialised.store(true, std::memory_order_release);
     return B200_OK;
 }
 
@@ -236,9 +314,14 @@ static void release_pinned_cache(); // (allocator, below)
 
 int b200_shutdown(void) {
     std::lock_guard<std::mutex> guard(g_lock);
-    if (!g_initialised)
+    if (!g_initialised.load(std::memory_order_acquire))
         return B200_OK;
     release_pinned_cache();
+    for (HistoryRecord &h : g_history) {
+        cudaEventDestroy(h.start);
+        cudaEventDestroy(h.end);
+    }
+    g_history.clear();
     for (size_t i = 0; i < g_devices.size(); ++i) {
         if (g_devices[i].stream) {
             cudaSetDevice((int) i);
@@ -248,7 +331,7 @@ int b200_shutdown(void) {
         }
     }
     g_devices.clear();
-    g_initialised = false;
+    g_initialised.store(false, std::memory_order_release);
     return B200_OK;
 }
 
@@ -257,6 +340,7 @@ const char *b200_last_error(void) { return tls_error.c_str(); }
 int b200_device_count(void) {
     if (ensure_init())
         return 0;
+    std::lock_guard<std::mutex> guard(g_lock);
     return (int) g_devices.size();
 }
 
@@ -264,9 +348,10 @@ int b200_set_device(int device) {
     int rc = ensure_init();
     if (rc)
         return rc;
-    if (device < 0 || device >= (int) g_devices.size())
+    int count = b200_device_count();
+    if (device < 0 || device >= count)
         return fail(B200_ERR_INVALID, "b200_set_device(%d): must be in the range 0..%d!",
-                    device, (int) g_devices.size() - 1);
+                    device, count - 1);
     B200_CUDA_CHECK(cudaSetDevice(device));
     return prepare_device(device);
 }
@@ -280,10 +365,7 @@ int b200_device(void) {
 void *b200_stream(void) {
     if (ensure_init())
         return nullptr;
-    int dev = current_device();
-    if (prepare_device(dev))
-        return nullptr;
-    return (void *) g_devices[dev].stream;
+    return (void *) library_stream();
 }
 
 int b200_sm_count(void) {
@@ -296,10 +378,67 @@ int b200_sync(void *stream) {
     int rc = ensure_init();
     if (rc)
         return rc;
-    cudaStream_t s = stream ? (cudaStream_t) stream : (cudaStream_t) b200_stream();
+    if ((rc = sync_forbidden()))
+        return rc;
+    cudaStream_t s = resolve_stream(stream);
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
     return B200_OK;
 }
+
+/* jit_cuda_sync_stream (jit.h:243-255; src/init.cpp): an event recorded on the
+ * library stream, 'other' waits for it.  2 = the caller's per-thread default stream. */
+int b200_sync_stream(void *other) {
+    int rc = ensure_init();
+    if (rc)
+        return rc;
+    cudaStream_t lib = library_stream();
+    cudaEvent_t ev;
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t err = cudaEventRecord(ev, lib);
+    if (err == cudaSuccess)
+        err = cudaStreamWaitEvent((cudaStream_t) other, ev, 0);
+    cudaEventDestroy(ev);
+    return cuda_fail(err, "jit_cuda_sync_stream()");
+}
+
+void b200_set_flags(uint32_t flags) { g_flags.store(flags, std::memory_order_relaxed); }
+uint32_t b200_flags(void) { return g_flags.load(std::memory_order_relaxed); }
+
+void b200_set_flag(uint32_t flag, int enable) {
+    if (enable)
+        g_flags.fetch_or(flag, std::memory_order_relaxed);
+    else
+        g_flags.fetch_and(~flag, std::memory_order_relaxed);
+}
+
+int b200_kernel_history(B200KernelRecord *out, int capacity) {
+    // like jit_kernel_history(): waits for the recorded events, hands the entries
+    // over and clears the history (src/init.cpp jitc_kernel_history)
+    std::vector<HistoryRecord> recs;
+    {
+        std::lock_guard<std::mutex> guard(g_lock);
+        recs.swap(g_history);
+    }
+    int n = 0;
+    for (HistoryRecord &h : recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(h.end);
+        cudaEventElapsedTime(&ms, h.start, h.end);
+        cudaEventDestroy(h.start);
+        cudaEventDestroy(h.end);
+        if (out && n < capacity) {
+            out[n].type = h.type;
+            out[n].size = h.size;
+            out[n].execution_time_ms = ms;
+        }
+        n++;
+    }
+    cudaGetLastError();
+    return n;
+}
+
+void b200_kernel_history_clear(void) { b200_kernel_history(nullptr, 0); }
+
 
 // Allocator contract of the reference (src/malloc.cpp:102-306):
 // sizes are rounded up to a power of two >= 64 bytes (compress and all / any of the
@@ -337,6 +476,7 @@ void *b200_malloc(size_t size, int kind) {
     while (rounded < size)
         rounded <<= 1;
     void *ptr = nullptr;
+    const int dev = current_device();
     if (kind == 1) {
         {
             std::lock_guard<std::mutex> guard(g_lock);
@@ -359,59 +499,118 @@ void *b200_malloc(size_t size, int kind) {
             }
         }
         std::lock_guard<std::mutex> guard(g_lock);
-        g_allocs[ptr] = kind;
+        g_allocs[ptr] = { kind, dev, nullptr, rounded };
         g_pinned_size[ptr] = rounded;
         return ptr;
     }
-    cudaStream_t s = (cudaStream_t) b200_stream();
-    retain_pool(current_device());
+    cudaStream_t s = library_stream();
+    retain_pool(dev);
     cudaError_t err = cudaMallocAsync(&ptr, rounded, s);
     if (err != cudaSuccess) {
         cuda_fail(err, "cudaMallocAsync");
         return nullptr;
     }
     std::lock_guard<std::mutex> guard(g_lock);
-    g_allocs[ptr] = kind;
+    g_allocs[ptr] = { kind, dev, s, rounded };
     return ptr;
 }
 
-int b200_free(void *ptr) {
+/// Release 'ptr' in the order of 'stream' (NULL: the library stream of the device
+/// the block was allocated on).  Work that uses the block on ANOTHER stream must
+/// be ordered before the release by the caller -- b200_free_on(that stream, ptr).
+static int free_impl(void *ptr, bool have_stream, cudaStream_t user_stream) {
     if (!ptr)
         return B200_OK;
-    int kind = -1;
+    AllocInfo info{};
     size_t pinned_size = 0;
     {
         std::lock_guard<std::mutex> guard(g_lock);
         auto it = g_allocs.find(ptr);
         if (it == g_allocs.end())
             return fail(B200_ERR_INVALID, "b200_free(): unknown address %p!", ptr);
-        kind = it->second;
+        info = it->second;
         g_allocs.erase(it);
-        if (kind == 1) {
+        if (info.kind == 1) {
             pinned_size = g_pinned_size[ptr];
             g_pinned_size.erase(ptr);
         }
     }
-    cudaStream_t s = (cudaStream_t) b200_stream();
-    if (kind == 1) {
+    // the block belongs to the device (and pool) it was allocated on, whatever device
+    // is current now
+    const int cur = current_device();
+    if (cur != info.device)
+        cudaSetDevice(info.device);
+    cudaStream_t s = have_stream ? user_stream : (info.stream ? info.stream : library_stream());
+    int rc = B200_OK;
+    if (info.kind == 1) {
         // reusable once the work enqueued so far (which may still read / write it) is done
         cudaEvent_t ev;
-        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        B200_CUDA_CHECK(cudaEventRecord(ev, s));
-        std::lock_guard<std::mutex> guard(g_lock);
-        g_pinned_cache[pinned_size].push_back({ ptr, ev });
+        cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (err == cudaSuccess)
+            err = cudaEventRecord(ev, s);
+        if (err == cudaSuccess) {
+            std::lock_guard<std::mutex> guard(g_lock);
+            g_pinned_cache[pinned_size].push_back({ ptr, ev });
+        } else {
+            rc = cuda_fail(err, "b200_free(): event");
+        }
     } else {
-        B200_CUDA_CHECK(cudaFreeAsync(ptr, s));
+        rc = cuda_fail(cudaFreeAsync(ptr, s), "cudaFreeAsync");
     }
-    return B200_OK;
+    if (cur != info.device)
+        cudaSetDevice(cur);
+    return rc;
+}
+
+int b200_free(void *ptr) { return free_impl(ptr, false, nullptr); }
+
+int b200_free_on(void *stream, void *ptr) {
+    return free_impl(ptr, stream != nullptr, (cudaStream_t) stream);
+}
+
+/* jit_malloc_migrate (jit.h:495-518) for the allocation kinds of this library:
+ * kind 0 = device, 1 = pinned host.  Same kind + move: returned unchanged.
+ * Otherwise a new block, an asynchronous copy on the library stream and (move)
+ * the release of the source, also in stream order. */
+void *b200_malloc_migrate(void *ptr, int kind, int move) {
+    if (!ptr || ensure_init())
+        return nullptr;
+    AllocInfo info{};
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> guard(g_lock);
+        auto it = g_allocs.find(ptr);
+        if (it == g_allocs.end()) {
+            fail(B200_ERR_INVALID, "jit_malloc_migrate(): unknown address %p!", ptr);
+            return nullptr;
+        }
+        info = it->second;
+        bytes = info.bytes;
+    }
+    if (info.kind == kind && (kind == 1 || info.device == current_device()) && move)
+        return ptr;
+    void *dst = b200_malloc(bytes, kind);
+    if (!dst)
+        return nullptr;
+    cudaStream_t s = library_stream();
+    if (cudaMemcpyAsync(dst, ptr, bytes, cudaMemcpyDefault, s) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "jit_malloc_migrate(): copy");
+        b200_free(dst);
+        return nullptr;
+    }
+    if (move)
+        b200_free(ptr);
+    return dst;
 }
 
 int b200_memcpy(void *dst, const void *src, size_t size) {
     int rc = ensure_init();
     if (rc)
         return rc;
+    if ((rc = sync_forbidden()))
+        return rc;
     // synchronous with respect to the library stream as well (jit_memcpy syncs)
-    cudaStream_t s = (cudaStream_t) b200_stream();
+    cudaStream_t s = resolve_stream(nullptr);
     B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, size, cudaMemcpyDefault, s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
     return B200_OK;
@@ -421,7 +620,8 @@ int b200_memcpy_async(void *stream, void *dst, const void *src, size_t size) {
     int rc = ensure_init();
     if (rc)
         return rc;
-    cudaStream_t s = stream ? (cudaStream_t) stream : (cudaStream_t) b200_stream();
+    cudaStream_t s = resolve_stream(stream);
+    HistoryScope hs(s, B200_KERNEL_MEMCPY, size);
     B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, size, cudaMemcpyDefault, s));
     return B200_OK;
 }
@@ -436,7 +636,8 @@ int b200_memset_async(void *stream, void *ptr, uint64_t size, uint32_t isize,
                     "jit_memset_async(): invalid element size (must be 1, 2, 4, or 8)!");
     if (size == 0)
         return B200_OK;
-    cudaStream_t s = stream ? (cudaStream_t) stream : (cudaStream_t) b200_stream();
+    cudaStream_t s = resolve_stream(stream);
+    HistoryScope hs(s, B200_KERNEL_MEMSET, size);
 
     // Patterns whose bytes are all equal collapse to a byte memset
     // (src/cuda_ts.cpp:143-148 does this for zero only)

@@ -427,6 +427,7 @@ int b200_block_prefix_reduce(void *stream_, int vt, int op, uint64_t size,
     if (((uintptr_t) in % tsize) != 0 || ((uintptr_t) out % tsize) != 0)
         return fail(B200_ERR_INVALID, "jit_block_prefix_reduce(): misaligned pointer!");
     cudaStream_t stream = resolve_stream(stream_);
+    HistoryScope hs(stream, B200_KERNEL_BLOCK_PREFIX_REDUCE, size);
     if (block_size == 1) {
         if (exclusive) {
             uint64_t ident = b200_reduce_identity(vt, op);

@@ -882,7 +882,9 @@ int b200_scatter_reduce(void *stream_, int vt, int op, int mode, void *target,
         return fail(B200_ERR_UNSUPPORTED, "jit_var_scatter(): unsupported reduction mode %d", mode);
     if (n == 0)
         return B200_OK;
-    ScatterCall call{ resolve_stream(stream_), target, value, index, mask, n, mode };
+    cudaStream_t stream = resolve_stream(stream_);
+    HistoryScope hs(stream, B200_KERNEL_SCATTER, n);
+    ScatterCall call{ stream, target, value, index, mask, n, mode };
     return fn(call);
 }
 
@@ -941,7 +943,16 @@ int b200_scatter_reduce_packet(void *stream_, int vt, int op, int mode, void *ta
     }
     if (n == 0)
         return B200_OK;
-    PacketCall call{ resolve_stream(stream_), target, values, width, index, mask, n, mode };
+    // red.global.add.v2 / .v4.f32 need 8- / 16-byte aligned packets (a misaligned
+    // address would raise a sticky misaligned-address fault)
+    if (vt == B200_VT_FLOAT32 && op == B200_OP_ADD && width >= 2 &&
+        ((uintptr_t) target % (std::min<uint32_t>(width, 4) * 4)) != 0)
+        return fail(B200_ERR_INVALID,
+                    "jit_var_scatter_packet(): the target of a float32 packet reduction must be "
+                    "aligned to %u bytes!", std::min<uint32_t>(width, 4) * 4);
+    cudaStream_t stream = resolve_stream(stream_);
+    HistoryScope hs(stream, B200_KERNEL_SCATTER, n);
+    PacketCall call{ stream, target, values, width, index, mask, n, mode };
     return fn(call);
 }
 

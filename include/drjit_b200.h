@@ -44,7 +44,23 @@ enum {
     B200_ERR_INVALID = 1,     /* reference: jitc_raise (bad size / block size) */
     B200_ERR_UNSUPPORTED = 2, /* reference: "no existing kernel for type=.., op=.." */
     B200_ERR_CUDA = 3,        /* reference: cuda_check -> jitc_fail */
-    B200_ERR_SYNC_FORBIDDEN = 4
+    B200_ERR_SYNC_FORBIDDEN = 4 /* reference: jitc_sync_thread under JitFlag::ForbidSynchronization,
+                                   src/init.cpp:503-505 */
+};
+
+/* JitFlag bits honoured on this path (jit.h:1734-1742, same values) */
+enum {
+    B200_FLAG_KERNEL_HISTORY = 1 << 15,        /* record every primitive call (b200_kernel_history) */
+    B200_FLAG_LAUNCH_BLOCKING = 1 << 16,       /* synchronise after every kernel launch */
+    B200_FLAG_FORBID_SYNCHRONIZATION = 1 << 17 /* blocking entry points fail with B200_ERR_SYNC_FORBIDDEN */
+};
+
+/* KernelType values of the kernel history (jit.h:2597-2634) */
+enum {
+    B200_KERNEL_BLOCK_REDUCE = 1, B200_KERNEL_BLOCK_PREFIX_REDUCE = 2, B200_KERNEL_DOT = 3,
+    B200_KERNEL_COMPRESS = 5, B200_KERNEL_MKPERM = 6, B200_KERNEL_MEMCPY = 7,
+    B200_KERNEL_MEMSET = 8,
+    B200_KERNEL_SCATTER = 64 /* stand-alone scatter kernels: fused into JIT kernels in the reference */
 };
 
 /* VarType values used on this path (jit.h:597-611) */
@@ -82,13 +98,41 @@ B200_API int b200_set_device(int device);        /* jit_cuda_set_device, src/ini
 B200_API int b200_device(void);
 B200_API void *b200_stream(void);                /* jit_cuda_stream, jit.h:192 */
 B200_API int b200_sync(void *stream);            /* jit_sync_thread, src/init.cpp:499+ */
+B200_API int b200_sync_stream(void *other);      /* jit_cuda_sync_stream, jit.h:243-255: 'other' waits for
+                                                    the work enqueued on the library stream so far */
 B200_API int b200_sm_count(void);
+
+/* jit_set_flags / jit_flags / jit_set_flag (jit.h:1815-1824) for the JitFlag bits
+ * above; other bits are stored and reported back but have no effect here. */
+B200_API void b200_set_flags(uint32_t flags);
+B200_API uint32_t b200_flags(void);
+B200_API void b200_set_flag(uint32_t flag, int enable);
+
+/* jit_kernel_history / jit_kernel_history_clear (jit.h:2636-2742): with
+ * B200_FLAG_KERNEL_HISTORY set every primitive call is bracketed by two events on
+ * its stream (CUDAThreadState::submit does that per launch, src/cuda_ts.cpp:23-46).
+ * Waits for the recorded calls, writes up to 'capacity' records, clears the
+ * history and returns the number of records there were. */
+typedef struct B200KernelRecord {
+    int type;                 /* B200_KERNEL_* (KernelType) */
+    uint64_t size;            /* KernelHistoryEntry::size */
+    float execution_time_ms;  /* KernelHistoryEntry::execution_time */
+} B200KernelRecord;
+B200_API int b200_kernel_history(B200KernelRecord *out, int capacity);
+B200_API void b200_kernel_history_clear(void);
 
 /* jit_malloc / jit_free (src/malloc.cpp:102-306): kind 0 = device, 1 = pinned
  * host.  Sizes are rounded like the reference (>= 64 B, next power of two,
  * src/malloc.cpp:113-124) so code that relied on that padding keeps working. */
 B200_API void *b200_malloc(size_t size, int kind);
+/* Released in the order of the stream (and on the device) the block was allocated
+ * on.  A block that was last used on ANOTHER stream is released with
+ * b200_free_on(that stream, ptr). */
 B200_API int b200_free(void *ptr);
+B200_API int b200_free_on(void *stream, void *ptr);
+/* jit_malloc_migrate (jit.h:495-518) between kind 0 (device) and 1 (pinned host);
+ * asynchronous on the library stream. */
+B200_API void *b200_malloc_migrate(void *ptr, int kind, int move);
 B200_API int b200_memcpy(void *dst, const void *src, size_t size);                       /* jit_memcpy, jit.h:2202 */
 B200_API int b200_memcpy_async(void *stream, void *dst, const void *src, size_t size);   /* jit_memcpy_async, jit.h:2205 */
 
@@ -185,6 +229,15 @@ B200_API int b200_compress_async(void *stream, const uint8_t *in, uint64_t size,
 B200_API int b200_block_mkperm(void *stream, const uint32_t *values, uint32_t size,
                                uint32_t block_size, uint32_t bucket_count,
                                uint32_t *perm, uint32_t *offsets, uint32_t *unique);
+
+/* Asynchronous form: everything is enqueued (including the copy of the records
+ * into 'offsets'), nothing is waited for; after the stream has been synchronised
+ * offsets[4 * bucket_count] holds the return value of the reference call.  This is
+ * what a host that holds a lock while enqueueing and drops it while waiting
+ * (state.lock / unlock_guard, src/cuda_ts.cpp:964-967) calls. */
+B200_API int b200_block_mkperm_async(void *stream, const uint32_t *values, uint32_t size,
+                                     uint32_t block_size, uint32_t bucket_count,
+                                     uint32_t *perm, uint32_t *offsets);
 
 /* Phase 1 of the above on its own (per-bucket counts of the whole array into
  * device memory hist[bucket_count]); the multi-GPU front end all-reduces it. */

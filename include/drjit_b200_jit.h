@@ -43,7 +43,51 @@ enum class ReduceOp : uint32_t { Identity, Add, Mul, Min, Max, And, Or, Count };
 /* jit.h:1017-1066 */
 enum class ReduceMode : uint32_t { Auto, Direct, Local, NoConflicts, Expand, Permute };
 
+/* jit.h:1734-1742 (the JitFlag bits this path honours; the other bits are stored
+ * and reported back by jit_flags() without effect) */
+enum class JitFlag : uint32_t {
+    KernelHistory = 1 << 15, LaunchBlocking = 1 << 16, ForbidSynchronization = 1 << 17
+};
+
+/* jit.h:2597-2634 */
+enum KernelType : uint32_t {
+    JIT, BlockReduce, BlockPrefixReduce, Dot, BatchedGemm, Compress, MkPerm, Memcpy, Memset,
+    Poke, Aggregate, LLVMHostFunc
+};
+
+/* jit.h:2636-2650 */
+enum KernelRecordingMode : uint32_t { Inactive, Recorded, Replayed };
+
+/* jit.h:2652-2709 (same layout) */
+struct KernelHistoryEntry {
+    JitBackend backend;
+    KernelType type;
+    KernelRecordingMode recording_mode;
+    uint64_t hash[2];
+    char *ir;
+    int uses_optix;
+    int cache_hit;
+    int cache_disk;
+    uint32_t size;
+    uint32_t input_count;
+    uint32_t output_count;
+    uint32_t operation_count;
+    float codegen_time;
+    float backend_time;
+    float execution_time;
+    void *event_start, *event_end;
+    void *task;
+};
+
 /* ---- runtime ------------------------------------------------------------ */
+extern DRJIT_B200_EXPORT void jit_cuda_sync_stream(uintptr_t stream);      /* jit.h:255 */
+extern DRJIT_B200_EXPORT void jit_set_flags(uint32_t flags);               /* jit.h:1815 */
+extern DRJIT_B200_EXPORT uint32_t jit_flags();                             /* jit.h:1818 */
+extern DRJIT_B200_EXPORT void jit_set_flag(JitFlag flag, int enable);      /* jit.h:1821 */
+extern DRJIT_B200_EXPORT int jit_flag(JitFlag flag);                       /* jit.h:1824 */
+extern DRJIT_B200_EXPORT void jit_kernel_history_clear();                  /* jit.h:2712 */
+extern DRJIT_B200_EXPORT KernelHistoryEntry *jit_kernel_history();         /* jit.h:2737 */
+extern DRJIT_B200_EXPORT void *jit_malloc_migrate(void *ptr, JitBackend backend, int move); /* jit.h:516 */
 extern DRJIT_B200_EXPORT void jit_init(uint32_t backends);                 /* jit.h:96 */
 extern DRJIT_B200_EXPORT int jit_has_backend(JitBackend backend);          /* jit.h:119 */
 extern DRJIT_B200_EXPORT void jit_shutdown(int light);                     /* jit.h:132 */

@@ -11,8 +11,21 @@
 // (tests/reductions.cpp, mem.cpp, vcall.cpp, record.cpp, ...) run on the sm_100a
 // kernels of this repository.  Nothing here is part of the product; no reference
 // source is copied: the file only includes the reference's headers where they lie.
+//
+// Semantics kept from the methods that are replaced:
+//   * JitFlag::KernelHistory -- one KernelHistoryEntry per forwarded primitive with
+//     the reference's KernelType and two events on the stream, appended to
+//     state.kernel_history (what submit() does per launch, src/cuda_ts.cpp:23-46),
+//     so jit_kernel_history() keeps listing the primitives;
+//   * JitFlag::LaunchBlocking -- the stream is synchronised after the call (:37-38);
+//   * compress: enqueue under state.lock, then jitc_sync_thread(this), which drops
+//     the lock while waiting and raises under JitFlag::ForbidSynchronization
+//     (src/cuda_ts.cpp:759, src/init.cpp:499-517); count read from pinned memory;
+//   * block_mkperm: enqueue under state.lock, wait on the thread state's event with
+//     the lock released (unlock_guard, src/cuda_ts.cpp:964-967).
 #include "cuda_ts.h"
 #include "var.h"
+#include "malloc.h"
 
 #include "../include/drjit_b200.h"
 
@@ -35,39 +48,87 @@ static void b200_check(int rc, const char *what) {
         jitc_raise("%s: %s", what, b200_last_error());
 }
 
+namespace {
+/// What submit() (src/cuda_ts.cpp:23-46) does around every precompiled kernel
+struct Submit {
+    CUstream stream;
+    uint32_t flags;
+    KernelHistoryEntry entry = {};
+
+    Submit(KernelType type, KernelRecordingMode mode, CUstream stream_, uint32_t width)
+        : stream(stream_), flags(jit_flags()) {
+        if (flags & (uint32_t) JitFlag::KernelHistory) {
+            cuda_check(cuEventCreate((CUevent *) &entry.event_start, CU_EVENT_DEFAULT));
+            cuda_check(cuEventCreate((CUevent *) &entry.event_end, CU_EVENT_DEFAULT));
+            cuda_check(cuEventRecord((CUevent) entry.event_start, stream));
+            entry.backend = JitBackend::CUDA;
+            entry.type = type;
+            entry.recording_mode = mode;
+            entry.size = width;
+            entry.input_count = 1;
+            entry.output_count = 1;
+        }
+    }
+
+    /// after the forwarded call has been enqueued
+    void done() {
+        if (flags & (uint32_t) JitFlag::LaunchBlocking)
+            cuda_check(cuStreamSynchronize(stream));
+        if (flags & (uint32_t) JitFlag::KernelHistory) {
+            cuda_check(cuEventRecord((CUevent) entry.event_end, stream));
+            state.kernel_history.append(entry);
+        }
+    }
+};
+} // namespace
+
 void CUDAThreadState::memset_async(void *ptr, uint32_t size, uint32_t isize, const void *src) {
     scoped_set_context guard(context);
+    Submit s(KernelType::Memset, recording_mode, stream, size);
     b200_check(b200_memset_async(stream, ptr, size, isize, src), "jit_memset_async()");
+    s.done();
 }
 
 void CUDAThreadState::block_reduce(VarType vt, ReduceOp op, uint32_t size, uint32_t block_size,
                                    const void *in, void *out) {
     scoped_set_context guard(context);
+    Submit s(KernelType::BlockReduce, recording_mode, stream, size);
     b200_check(b200_block_reduce(stream, (int) vt, (int) op, size, block_size, in, out),
                "jit_block_reduce()");
+    s.done();
 }
 
 void CUDAThreadState::block_prefix_reduce(VarType vt, ReduceOp op, uint32_t size,
                                           uint32_t block_size, bool exclusive, bool reverse,
                                           const void *in, void *out) {
     scoped_set_context guard(context);
+    Submit s(KernelType::BlockPrefixReduce, recording_mode, stream, size);
     b200_check(b200_block_prefix_reduce(stream, (int) vt, (int) op, size, block_size, exclusive,
                                         reverse, in, out),
                "jit_block_prefix_reduce()");
+    s.done();
 }
 
 void CUDAThreadState::reduce_dot(VarType vt, const void *ptr_1, const void *ptr_2, uint32_t size,
                                  void *out) {
     scoped_set_context guard(context);
+    Submit s(KernelType::Dot, recording_mode, stream, size);
     b200_check(b200_reduce_dot(stream, (int) vt, ptr_1, ptr_2, size, out), "jit_reduce_dot()");
+    s.done();
 }
 
 uint32_t CUDAThreadState::compress(const uint8_t *in, uint32_t size, uint32_t *out) {
     if (size == 0)
         return 0;
     scoped_set_context guard(context);
-    uint32_t count = 0;
-    b200_check(b200_compress(stream, in, size, out, &count), "jit_compress()");
+    // the count lands in pinned memory (the reference: AllocType::HostPinned count_out)
+    uint32_t *count_out = (uint32_t *) jitc_malloc(backend, sizeof(uint32_t), /* shared = */ true);
+    Submit s(KernelType::Compress, recording_mode, stream, size);
+    b200_check(b200_compress_async(stream, in, size, out, count_out), "jit_compress()");
+    s.done();
+    jitc_sync_thread(this); // releases state.lock while waiting; raises if synchronisation is forbidden
+    uint32_t count = *count_out;
+    jitc_free(count_out);
     return count;
 }
 
@@ -78,9 +139,16 @@ uint32_t CUDAThreadState::block_mkperm(const uint32_t *values, uint32_t size, ui
     if (bucket_count == 0)
         jitc_fail("jit_block_mkperm(): bucket_count cannot be zero!");
     scoped_set_context guard(context);
-    uint32_t unique = 0;
-    b200_check(b200_block_mkperm(stream, values, size, block_size, bucket_count, perm, offsets,
-                                 &unique),
+    Submit s(KernelType::MkPerm, recording_mode, stream, size);
+    b200_check(b200_block_mkperm_async(stream, values, size, block_size, bucket_count, perm, offsets),
                "jit_block_mkperm()");
-    return unique;
+    s.done();
+    const bool one_group = block_size >= size;
+    if (offsets && one_group) {
+        cuda_check(cuEventRecord(this->event, stream));
+        unlock_guard guard_2(state.lock);
+        cuda_check(cuEventSynchronize(this->event));
+        return offsets[4 * (size_t) bucket_count];
+    }
+    return 0u;
 }

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -180,6 +181,108 @@ int main() {
         }
         CHECK(thrown, "non-CUDA backend must throw (no CPU fallback)");
         tests += 2;
+    }
+    // flags of the boundary (SURVEY.md 8b "Ordering / sync"; jit.h:1734-1742, :1815-1824)
+    {
+        const uint32_t n = 100000;
+        std::vector<uint32_t> h(n);
+        std::vector<uint8_t> hm(n);
+        uint32_t total = 0, expect_count = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            h[k] = mix(k);
+            total += h[k];
+            hm[k] = (mix(k) & 7) == 0;
+            expect_count += hm[k];
+        }
+        Dev<uint32_t> d_in(n), d_out(n);
+        Dev<uint8_t> d_mask(2 * n);
+        d_in.put(h);
+        d_mask.put(hm);
+        const uint32_t flags0 = jit_flags();
+
+        // KernelHistory: every primitive call shows up with its KernelType
+        jit_kernel_history_clear();
+        jit_set_flag(JitFlag::KernelHistory, 1);
+        CHECK(jit_flag(JitFlag::KernelHistory) == 1, "jit_flag(KernelHistory)");
+        jit_block_reduce(JitBackend::CUDA, VarType::UInt32, ReduceOp::Add, n, n, d_in.ptr, d_out.ptr);
+        jit_block_prefix_reduce(JitBackend::CUDA, VarType::UInt32, ReduceOp::Add, n, n, 1, 0, d_in.ptr, d_out.ptr);
+        uint32_t cnt = jit_compress(JitBackend::CUDA, d_mask.ptr, n, d_out.ptr);
+        jit_block_mkperm(JitBackend::CUDA, d_in.ptr, n, n, 0xffffffffu, d_out.ptr, nullptr);
+        jit_set_flag(JitFlag::KernelHistory, 0);
+        KernelHistoryEntry *hist = jit_kernel_history();
+        CHECK(hist != nullptr, "kernel history is empty");
+        bool seen[4] = { false, false, false, false };
+        size_t entries = 0;
+        for (KernelHistoryEntry *e = hist; e && (uint32_t) e->backend; ++e, ++entries) {
+            CHECK(e->backend == JitBackend::CUDA && e->size == n && e->execution_time >= 0.f, "history entry");
+            if (e->type == KernelType::BlockReduce) seen[0] = true;
+            if (e->type == KernelType::BlockPrefixReduce) seen[1] = true;
+            if (e->type == KernelType::Compress) seen[2] = true;
+            if (e->type == KernelType::MkPerm) seen[3] = true;
+            free(e->ir);
+        }
+        free(hist);
+        CHECK(entries >= 4 && seen[0] && seen[1] && seen[2] && seen[3], "history types (%zu entries)", entries);
+        CHECK(cnt == expect_count, "compress under KernelHistory");
+        CHECK(jit_kernel_history() == nullptr, "jit_kernel_history() must clear the history");
+        tests += 5;
+
+        // LaunchBlocking: the result is there when the call returns
+        jit_set_flag(JitFlag::LaunchBlocking, 1);
+        uint32_t *pinned = (uint32_t *) jit_malloc(JitBackend::CUDA, 64, 1);
+        pinned[0] = 0;
+        jit_block_reduce(JitBackend::CUDA, VarType::UInt32, ReduceOp::Add, n, n, d_in.ptr, pinned);
+        CHECK(pinned[0] == total, "LaunchBlocking: result must be visible without a sync");
+        jit_set_flag(JitFlag::LaunchBlocking, 0);
+        jit_free(pinned);
+        tests++;
+
+        // ForbidSynchronization: the synchronising entry points raise (src/init.cpp:503-505),
+        // the asynchronous ones keep working
+        jit_set_flag(JitFlag::ForbidSynchronization, 1);
+        bool thrown = false;
+        try {
+            jit_compress(JitBackend::CUDA, d_mask.ptr, n, d_out.ptr);
+        } catch (const std::runtime_error &) {
+            thrown = true;
+        }
+        CHECK(thrown, "jit_compress must throw under ForbidSynchronization");
+        thrown = false;
+        try {
+            jit_sync_thread();
+        } catch (const std::runtime_error &) {
+            thrown = true;
+        }
+        CHECK(thrown, "jit_sync_thread must throw under ForbidSynchronization");
+        thrown = false;
+        try {
+            jit_block_reduce(JitBackend::CUDA, VarType::UInt32, ReduceOp::Add, n, n, d_in.ptr, d_out.ptr);
+        } catch (const std::runtime_error &) {
+            thrown = true;
+        }
+        CHECK(!thrown, "asynchronous primitives must not throw under ForbidSynchronization");
+        jit_set_flag(JitFlag::ForbidSynchronization, 0);
+        CHECK(d_out.get(1)[0] == total, "reduce enqueued under ForbidSynchronization");
+        jit_set_flags(flags0);
+        CHECK(jit_flags() == flags0, "jit_set_flags / jit_flags");
+        tests += 5;
+
+        // jit_malloc_migrate (jit.h:516): device -> host copy, host -> device move
+        uint32_t *host = (uint32_t *) jit_malloc_migrate(d_in.ptr, JitBackend::None, 0);
+        jit_sync_thread();
+        CHECK(host && host != d_in.ptr && std::memcmp(host, h.data(), n * sizeof(uint32_t)) == 0,
+              "jit_malloc_migrate to the host");
+        uint32_t *dev2 = (uint32_t *) jit_malloc_migrate(host, JitBackend::CUDA, 1);
+        jit_block_reduce(JitBackend::CUDA, VarType::UInt32, ReduceOp::Add, n, n, dev2, d_out.ptr);
+        CHECK(d_out.get(1)[0] == total, "jit_malloc_migrate back to the device");
+        CHECK(jit_malloc_migrate(dev2, JitBackend::CUDA, 1) == dev2, "migrate to the same place is a no-op");
+        jit_free(dev2);
+        tests += 3;
+
+        // jit_cuda_sync_stream (jit.h:243-255): the per-thread default stream (2) waits
+        jit_block_reduce(JitBackend::CUDA, VarType::UInt32, ReduceOp::Add, n, n, d_in.ptr, d_out.ptr);
+        jit_cuda_sync_stream(2);
+        tests++;
     }
     jit_shutdown(0);
     printf("jit_h_client: %d checks, %d failed\n", tests, failures);

@@ -218,3 +218,19 @@ def test_mkperm_full_size(dr, O):
         assert uq == ruq
         assert np.array_equal(offs[:4 * uq], roffs[:4 * ruq])
         assert np.array_equal(perm, rperm)
+
+
+def test_compress_nonbinary_mask_bytes(dr):
+    # jit.h:2377-2379 defines only 0 / 1 mask bytes; every non-zero byte selects the
+    # entry on BOTH code paths of jit_compress (single pass <= 32768 < bit-packed tiles)
+    from cases import fmix32
+    bad = []
+    for size in (1000, 32768, 32769, 100003, (1 << 20) + 5):
+        h = fmix32(np.arange(size, dtype=np.uint32))
+        m = np.where((h & np.uint32(3)) == 0, np.uint8(0), (h >> np.uint32(8)).astype(np.uint8))
+        # bytes like 0x02, 0x80, 0xfe appear; a few become 0 by chance -- that is the definition
+        expect = np.flatnonzero(m).astype(np.uint32)
+        idx, cnt = run_compress(dr, m)
+        if cnt != expect.size or not np.array_equal(idx, expect):
+            bad.append((size, cnt, expect.size))
+    assert not bad, bad
