@@ -330,7 +330,7 @@ def run_b200_arm(args):
 
     from importlib import import_module
     sharded_mod = import_module("drjit_core_b200.sharded")
-    sh = sharded_mod.Sharded(device=dev)
+    sh = sharded_mod.Sharded(device=dev, exchange=args.exchange)
 
     n = 1 << args.log2n
     n_global = n * world
@@ -462,7 +462,24 @@ def run_b200_arm(args):
         del out
         torch.cuda.empty_cache()
         if world == 1:
-            line["primitives"] = measure_primitives(torch, dr, dev, peak)
+            prim = measure_primitives(torch, dr, dev, peak)
+            line["primitives"] = prim
+            step2 = prim.pop("_step_compress_mkperm")
+            line["value_all_primitives"] = {
+                "value": (len(calls) * n + 3 * (1 << 28) + 3 * (1 << 26)) / ((ms_per_step + step2["ms"]) * 1e-3),
+                "unit": "elements/s",
+                "note": "the headline step (28 reduce / scan calls) plus the compress / mkperm step, "
+                        "elements of both divided by the sum of both times",
+                "step_compress_mkperm": step2}
+            # worst primitive at the BASELINE sizes (the north_star bar is 0.8 for every one)
+            fr = {k: v["frac"] for k, v in prim.items() if "frac" in v}
+            fr.update({f"step:{k}": v["frac"] for k, v in per_call_report.items()})
+            worst = min(fr, key=fr.get)
+            line["roofline_min"] = {"name": worst, "frac": fr[worst],
+                                    "by_family": {fam: min(v for k, v in fr.items() if fam in k)
+                                                  for fam in ("reduce", "scan", "prefix_sum", "compress",
+                                                              "mkperm", "scatter_add", "scatter_inc")
+                                                  if any(fam in k for k in fr)}}
         if not args.no_sharded:
             line["sharded"] = measure_sharded(torch, dr, dist, sh, world, rank, dev, peak, barrier)
 
@@ -575,6 +592,7 @@ def measure_primitives(torch, dr, dev, peak):
     # compress (C3): mask[i] = fmix32(i ^ 0x9E3779B9) < d * 2^32
     h = torch.empty(n, dtype=torch.int32, device=dev)
     fill_input(torch, out_u32=h, xor=0x9E3779B9)
+    masks = {}
     for d in (0.01, 0.5, 0.99):
         thr = int(d * 2 ** 32)
         mask = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -586,18 +604,39 @@ def measure_primitives(torch, dr, dev, peak):
         ms = time_call(torch, lambda: dr.jit_compress(CUDA, mask, n, oi))
         rec(f"compress_2^28_d{d}", ms, n, n + 4 * cnt)
         res[f"compress_2^28_d{d}"]["count"] = int(cnt)
-        del mask
+        masks[d] = (mask, int(cnt))
     del h
 
     # mkperm (C4): key[i] = fmix32(i) % B, n = 2^26, one group, offsets requested
     n2 = 1 << 26
     keys = torch.empty(n2, dtype=torch.int32, device=dev)
     perm = oi[:n2]
+    mk = {}
     for B in (16, 1024, 65536):
-        fill_input(torch, out_u32=keys, mod=B)
+        kB = torch.empty(n2, dtype=torch.int32, device=dev)
+        fill_input(torch, out_u32=kB, mod=B)
         offs = torch.zeros(4 * B + 1, dtype=torch.int32).pin_memory()
-        ms = time_call(torch, lambda: dr.jit_block_mkperm(CUDA, keys, n2, n2, B, perm, offs))
+        ms = time_call(torch, lambda: dr.jit_block_mkperm(CUDA, kB, n2, n2, B, perm, offs))
         rec(f"mkperm_2^26_B{B}", ms, n2, 8 * n2)
+        mk[B] = (kB, offs)
+
+    # second timed step: the OTHER primitives of BASELINE.json's metric back to back
+    # (configs[2] + configs[3]: compress x3 densities at 2^28, mkperm x3 bucket counts at 2^26)
+    def step2():
+        for d, (mask, _) in masks.items():
+            dr.jit_compress(CUDA, mask, n, oi)
+        for B, (kB, offs) in mk.items():
+            dr.jit_block_mkperm(CUDA, kB, n2, n2, B, perm, offs)
+
+    ms2 = time_call(torch, step2, iters=5, warmup=3)
+    elems2 = 3 * n + 3 * n2
+    bytes2 = sum(n + 4 * c for _, c in masks.values()) + 3 * 8 * n2
+    res["_step_compress_mkperm"] = {"ms": ms2, "elements_per_s": elems2 / (ms2 * 1e-3),
+                                    "GBs": bytes2 / (ms2 * 1e-3) / 1e9,
+                                    "frac": bytes2 / (ms2 * 1e-3) / 1e9 / peak,
+                                    "calls": "jit_compress 2^28 x {0.01, 0.5, 0.99} + jit_block_mkperm 2^26 x "
+                                             "{16, 1024, 65536} buckets (with offsets), synchronous calls"}
+    del masks, mk
 
     # scatter-add (C5): 2^26 -> 2^20, random and coherent indices
     m = 1 << 20
@@ -626,11 +665,43 @@ def measure_primitives(torch, dr, dev, peak):
     return res
 
 
+def load_sharded_basis():
+    """N = 1 times of the sharded workload from the committed 1-GPU run
+    (profiles/sharded_n1_basis.json), so that an N > 1 line carries its own
+    strong-scaling figures."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "sharded_n1_basis.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def timed_collective(torch, dist, dev, world, barrier, fn, iters=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t.item()))
+    return float(np.median(ts))
+
+
 def measure_sharded(torch, dr, dist, sh, world, rank, dev, peak, barrier):
     """BASELINE configs[4]: 2^32 fp32 elements in total, contiguous shards of
-    2^32 / N per GPU; whole-array reduce and exclusive scan.  At N = 1 the array
-    exceeds the uint32 sizes of the reference API: it is processed as chunks of
-    2^31 chained through the carry entry point of the C-ABI."""
+    2^32 / N per GPU; whole-array reduce and exclusive scan, plus the mkperm histogram
+    of 2^26 keys per rank.  At N = 1 the array exceeds the uint32 sizes of the reference
+    API: it is processed as chunks of 2^31 chained through the carry entry point of the
+    C-ABI.  `parity` = the sharded results were checked on the device against an
+    independent torch computation (u32 bit-exact, fp32 within 1e-5)."""
     total = 1 << 32
     n_local = total // world
     x = torch.empty(n_local, dtype=torch.float32, device=dev)
@@ -655,40 +726,102 @@ def measure_sharded(torch, dr, dist, sh, world, rank, dev, peak, barrier):
         else:
             sh.prefix_reduce(F32, ADD, x, n_local, True, False, out)
 
-    res = {"total_elements": total, "elements_per_gpu": n_local, "scaling": "strong"}
+    res = {"total_elements": total, "elements_per_gpu": n_local, "scaling": "strong",
+           "exchange": "peer mailboxes over NVLink (csrc/sharded.cu)" if sh.peer is not None
+           else ("nccl all_gather" if world > 1 else "single GPU")}
     for name, fn, bpe in (("reduce", do_reduce, 4), ("exclusive_scan", do_scan, 8)):
-        for _ in range(2):
-            fn()
-        ts = []
-        for _ in range(5):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            torch.cuda.synchronize()
-            a.record()
-            fn()
-            b.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ts.append(float(t.item()))
-        ms = float(np.median(ts))
+        ms = timed_collective(torch, dist, dev, world, barrier, fn)
         gbs = bpe * total / (ms * 1e-3) / 1e9
         res[name] = {"ms": ms, "elements_per_s": total / (ms * 1e-3), "GBs_aggregate": gbs,
                      "frac_of_n_gpu_peak": gbs / (peak * world)}
     torch.cuda.synchronize()
     res["reduce_value"] = float(res_buf[0].item())
-    # sanity of the sharded exclusive scan (not a parity test -- those are in tests/):
-    # the last element of the last shard plus the last input is the global sum
-    last = torch.zeros(2, dtype=torch.float64, device=dev)
-    if rank == world - 1:
-        last[0] = out[-1].double() + x[-1].double()
-        last[1] = 1.0
+
+    # ---- parity of the fp32 results (every prefix of this shard, fp64 reference on the device)
+    parity = True
+    tot64 = torch.zeros(world, dtype=torch.float64, device=dev)
+    tot64[rank] = x.sum(dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(last, op=dist.ReduceOp.SUM)
-    res["scan_last_plus_input"] = float(last[0].item())
-    res["scan_consistent_with_reduce"] = bool(
-        abs(res["scan_last_plus_input"] - res["reduce_value"]) <= 1e-4 * abs(res["reduce_value"]))
+        dist.all_reduce(tot64)
+    ref_total = float(tot64.sum().item())
+    parity &= abs(res["reduce_value"] - ref_total) <= 1e-5 * ref_total
+    carry64 = float(tot64[:rank].sum().item())
+    worst = 0.0
+    step = 1 << 27
+    run = carry64
+    for s0 in range(0, n_local, step):
+        seg = x[s0:s0 + step].double()
+        inc = torch.cumsum(seg, 0)
+        ref = inc - seg + run
+        err = ((out[s0:s0 + step].double() - ref).abs() / ref.abs().clamp_min(1.0)).max()
+        worst = max(worst, float(err.item()))
+        run += float(inc[-1].item())
+        del seg, inc, ref
+    res["scan_max_rel_err_vs_fp64"] = worst
+    parity &= worst <= 1e-5
+    del x, out
+    torch.cuda.empty_cache()
+
+    # ---- u32, bit-exact: reduce + exclusive scan over 2^26 elements per rank
+    M = 0xFFFFFFFF
+    n_u = 1 << 26
+    xu = torch.empty(n_u, dtype=torch.int32, device=dev)
+    fill_input(torch, out_u32=xu, start=rank * n_u)
+    ou = torch.empty(n_u, dtype=torch.int32, device=dev)
+    ru = torch.zeros(4, dtype=torch.int32, device=dev)
+    if world == 1:
+        dr.jit_reduce(CUDA, U32, ADD, xu, n_u, ru)
+        dr.jit_block_prefix_reduce(CUDA, U32, ADD, n_u, n_u, 1, 0, xu, ou)
+    else:
+        sh.reduce(U32, ADD, xu, n_u, ru)
+        sh.prefix_reduce(U32, ADD, xu, n_u, True, False, ou)
+    torch.cuda.synchronize()
+    xl = xu.to(torch.int64) & M
+    tots = torch.zeros(world, dtype=torch.int64, device=dev)
+    tots[rank] = xl.sum() & M
+    if world > 1:
+        dist.all_reduce(tots)
+    parity &= (int(ru[0].item()) & M) == (int(tots.sum().item()) & M)
+    ref = (torch.cumsum(xl, 0) - xl + (int(tots[:rank].sum().item()) & M)) & M
+    parity &= bool(torch.equal(ou.to(torch.int64) & M, ref))
+    del xl, ref, ou, xu
+
+    # ---- mkperm histogram: 2^26 keys per rank, global counts on every rank
+    keys = torch.empty(n_u, dtype=torch.int32, device=dev)
+    res["mkperm_histogram"] = {"keys_per_gpu": n_u}
+    for B in (16, 1024, 65536):
+        fill_input(torch, out_u32=keys, start=rank * n_u, mod=B)
+        hist_local = torch.zeros(B, dtype=torch.int32, device=dev)
+        holder = {}
+
+        def do_hist():
+            if world == 1:
+                dr.mkperm_histogram(keys, n_u, B, hist_local)
+                holder["h"] = hist_local
+            else:
+                holder["h"] = sh.mkperm_histogram(keys, n_u, B)
+
+        ms = timed_collective(torch, dist, dev, world, barrier, do_hist)
+        refh = torch.bincount(keys.to(torch.int64), minlength=B)
+        if world > 1:
+            dist.all_reduce(refh)
+        parity &= bool(torch.equal(holder["h"].to(torch.int64), refh))
+        gbs = 4.0 * n_u * world / (ms * 1e-3) / 1e9
+        res["mkperm_histogram"][f"B{B}"] = {"ms": ms, "keys_per_s": n_u * world / (ms * 1e-3),
+                                            "GBs_aggregate": gbs, "frac_of_n_gpu_peak": gbs / (peak * world)}
+    flag = torch.tensor([1 if parity else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["parity"] = bool(int(flag.item()))
+    res["parity_checks"] = ("fp32 2^32: reduce and EVERY exclusive prefix within 1e-5 of fp64; u32 2^26/rank: "
+                            "reduce and exclusive scan bit-exact; mkperm histogram 16/1024/65536 buckets "
+                            "bit-exact (independent torch reference on the device)")
+
+    basis = load_sharded_basis()
+    if basis:
+        res["speedup_basis_ms"] = basis
+        res["speedup_vs_1gpu"] = {k: basis[k] / res[k]["ms"] for k in ("reduce", "exclusive_scan")
+                                  if k in basis}
     return res
 
 
@@ -702,6 +835,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-primitives", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="how the sharded primitives exchange their totals (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -111,6 +111,13 @@ def lib():
         L.b200_scatter_reduce.argtypes = [vp, i, i, i, vp, vp, vp, vp, u64]
         L.b200_scatter_inc.argtypes = [vp, vp, vp, vp, vp, u64]
         L.b200_scatter_reduce_packet.argtypes = [vp, i, i, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
+        L.b200_sharded_create.argtypes = [i, i, ctypes.POINTER(vp)]
+        L.b200_sharded_export.argtypes = [vp, vp]
+        L.b200_sharded_connect.argtypes = [vp, vp]
+        L.b200_sharded_destroy.argtypes = [vp]
+        L.b200_sharded_reduce.argtypes = [vp, vp, i, i, vp, u64, vp]
+        L.b200_sharded_prefix_reduce.argtypes = [vp, vp, i, i, u64, i, i, vp, vp]
+        L.b200_sharded_histogram.argtypes = [vp, vp, vp, u64, u32, vp, vp]
         L.b200_all_async.argtypes = [vp, vp, u64, vp]
         L.b200_any_async.argtypes = [vp, vp, u64, vp]
         L.b200_all.argtypes = [vp, vp, u64, ctypes.POINTER(i)]
@@ -400,3 +407,41 @@ def jit_any(backend, values, size, stream=None):
     r = ctypes.c_int(0)
     _check(lib().b200_any(_stream(stream), _ptr(values), size, ctypes.byref(r)))
     return bool(r.value)
+
+
+# ---- multi-GPU: peer-mapped mailboxes (include/drjit_b200.h, "multi-GPU") ------------
+class ShardedContext:
+    """b200_sharded_*: one context per rank.  `gather_handles(my_handle: bytes) ->
+    list[bytes]` exchanges the CUDA IPC handles of the mailboxes (all ranks, rank
+    order) over whatever channel the host program has (torch.distributed, MPI, ...)."""
+
+    def __init__(self, rank, world, gather_handles):
+        self.rank, self.world = rank, world
+        ctx = ctypes.c_void_p()
+        _check(lib().b200_sharded_create(rank, world, ctypes.byref(ctx)))
+        self._ctx = ctx
+        nbytes = lib().b200_sharded_handle_bytes()
+        mine = (ctypes.c_uint8 * nbytes)()
+        _check(lib().b200_sharded_export(self._ctx, mine))
+        handles = gather_handles(bytes(mine))
+        assert len(handles) == world and all(len(h) == nbytes for h in handles)
+        blob = (ctypes.c_uint8 * (nbytes * world)).from_buffer_copy(b"".join(handles))
+        _check(lib().b200_sharded_connect(self._ctx, blob))
+
+    def close(self):
+        if self._ctx:
+            lib().b200_sharded_destroy(self._ctx)
+            self._ctx = None
+
+    def reduce(self, vt, op, in_, local_size, out, stream=None):
+        _check(lib().b200_sharded_reduce(self._ctx, _stream(stream), vt, op, _ptr(in_), local_size,
+                                         _ptr(out)))
+
+    def prefix_reduce(self, vt, op, local_size, exclusive, reverse, in_, out, stream=None):
+        _check(lib().b200_sharded_prefix_reduce(self._ctx, _stream(stream), vt, op, local_size,
+                                                int(bool(exclusive)), int(bool(reverse)), _ptr(in_),
+                                                _ptr(out)))
+
+    def histogram(self, values, local_size, bucket_count, hist, before=None, stream=None):
+        _check(lib().b200_sharded_histogram(self._ctx, _stream(stream), _ptr(values), local_size,
+                                            bucket_count, _ptr(hist), _ptr(before)))

@@ -309,146 +309,64 @@ mkperm_bounds_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restri
 
 // ------------------------------------------------ single sorting group: tiles
 //
-// block_size == size (what vectorised method dispatch passes): the array is cut
-// into tiles of 8192 keys.
-//   tile_hist   per-tile digit counts, written digit-major (table[d][tile]) so
+// block_size == size (what vectorised method dispatch passes) and every block_size
+// of at least half a tile: the array is cut into tiles of 8192 keys that never cross
+// a sorting group, a tile into two HALVES of 4096 keys (the keys of the lower / upper
+// half of the ranking kernel's threads).
+//   tile_hist   per-half digit counts, written digit-major (table[d][tile][half]) so
 //               that ONE exclusive scan of the flattened table (scan_fast.cu)
-//               yields the first output slot of every (digit, tile) pair;
+//               yields the first output slot of every (digit, tile, half) triple;
 //   rank_place  re-reads the tile, ranks its keys stably, sorts the tile by digit
-//               in shared memory and writes every digit's run with a bulk copy
+//               in shared memory and writes every digit's two runs with bulk copies
 //               (further down).  The per-row variant above has every warp
 //               trickle single elements into `bins` output streams at once,
 //               which thrashes L2 (measured on B200: 6.5x DRAM write
 //               amplification, 2-4 ms for 2^26 keys).
+// Any radix pass has to see ALL keys before it can place the first one (the first
+// slot of bucket 1 is the number of keys in bucket 0), so with keys far beyond the
+// on-chip memories a pass moves at least 4 (count) + 4 (rank) + 4 (write) bytes per
+// key: 12 B/key, not the 8 B/key of the permutation's inputs and outputs.
 static constexpr int MT_THREADS = 512;
-static constexpr int MT_ITEMS = 16;
-static constexpr uint32_t MT_TILE = MT_THREADS * MT_ITEMS; // 8192 keys
 static constexpr uint32_t MT_MAX_BINS = 64;                // 6-bit digits
-
-B200_DEVICE uint32_t mt_digit(uint32_t key, uint32_t shift, uint32_t mask, uint32_t bins) {
-    return min((key >> shift) & mask, bins - 1); // out-of-range keys must not corrupt memory
-}
-
-/// table[table_index(tile, d)] = number of keys of the tile whose digit is d.  A CTA
-/// counts MT_GROUP consecutive tiles into one shared-memory histogram each, so
-/// that the MT_GROUP entries of a digit are contiguous in the digit-major table
-/// (one 32-byte run instead of MT_GROUP scattered words).
-/// Dynamic shared memory: MT_GROUP * bins counters.
-static constexpr uint32_t MT_GROUP = 8;
+static constexpr uint32_t MT_GROUP = 16;                   // half tiles counted by one CTA
 
 /// Tiles of the ranked path never cross a sorting group: group g owns the tiles
 /// [g * tpg, (g + 1) * tpg), the last tile of a group may be short.  One group:
 /// group_size = size, tpg = number of tiles.
 struct TileGeom {
-    uint64_t size;        // keys in total
+    uint32_t size;        // keys in total
     uint32_t group_size;  // keys per sorting group
     uint32_t tpg;         // tiles per group
     uint32_t ntiles;      // tiles in total
 };
 
-/// First key and number of keys of a tile
-B200_DEVICE void tile_range(const TileGeom &g, uint32_t tile, uint64_t &base, uint32_t &count) {
+/// First key and number of keys of a tile of TILE keys
+template <uint32_t TILE>
+B200_DEVICE void tile_range(const TileGeom &g, uint32_t tile, uint32_t &base, uint32_t &count) {
+    if (g.tpg == g.ntiles) { // one group: no division
+        base = tile * TILE;
+        count = min(TILE, g.size - base);
+        return;
+    }
     const uint32_t grp = tile / g.tpg, tg = tile - grp * g.tpg;
-    const uint64_t gstart = (uint64_t) grp * g.group_size;
-    const uint64_t gend = min(gstart + g.group_size, g.size);
-    base = gstart + (uint64_t) tg * MT_TILE;
-    count = base < gend ? (uint32_t) min((uint64_t) MT_TILE, gend - base) : 0u;
+    const uint32_t gstart = grp * g.group_size; // (the last group starts below 2^32)
+    const uint32_t glen = min(g.group_size, g.size - gstart);
+    const uint32_t off = tg * TILE;
+    base = gstart + off;
+    count = off < glen ? min(TILE, glen - off) : 0u;
 }
 
-/// Position of (tile, digit) in the count table: [group][digit][tile of the group],
-/// so that an exclusive scan in blocks of bins * tpg entries yields the first
-/// output slot of every (digit, tile) pair relative to its group.
+/// Position of (tile, half 0, digit) in the count table: [group][digit][tile of the
+/// group][half], so that an exclusive scan in blocks of bins * tpg * 2 entries yields
+/// the first output slot of every (digit, tile, half) triple relative to its group.
 B200_DEVICE uint64_t table_index(const TileGeom &g, uint32_t tile, uint32_t digit, uint32_t bins) {
+    if (g.tpg == g.ntiles)
+        return ((uint64_t) digit * g.ntiles + tile) * 2;
     const uint32_t grp = tile / g.tpg, tg = tile - grp * g.tpg;
-    return ((uint64_t) grp * bins + digit) * g.tpg + tg;
+    return (((uint64_t) grp * bins + digit) * g.tpg + tg) * 2;
 }
 
-__global__ void __launch_bounds__(MT_THREADS)
-mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, const TileGeom g,
-                        uint32_t shift, uint32_t mask, uint32_t bins,
-                        uint32_t *__restrict__ table) {
-    extern __shared__ uint32_t mk_smem[];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t tile0 = blockIdx.x * MT_GROUP;
-    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS)
-        mk_smem[i] = 0;
-    __syncthreads();
-    #pragma unroll 1
-    for (uint32_t t = 0; t < MT_GROUP; t += 2) {
-        // two tiles per step: 8 x 16-byte loads in flight per thread
-        uint4 k4[2][MT_ITEMS / 4];
-        bool full[2];
-        uint64_t base[2];
-        uint32_t count[2];
-        #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            base[u] = 0;
-            count[u] = 0;
-            if (tile0 + t + u < g.ntiles)
-                tile_range(g, tile0 + t + u, base[u], count[u]);
-            full[u] = count[u] == MT_TILE && ((uintptr_t) (keys + base[u]) & 15) == 0;
-            if (full[u]) {
-                const uint4 *v = (const uint4 *) (keys + base[u]);
-                #pragma unroll
-                for (int j = 0; j < MT_ITEMS / 4; ++j)
-                    k4[u][j] = ld_stream(v + j * MT_THREADS + tid);
-            }
-        }
-        #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            uint32_t *h = mk_smem + (t + u) * bins;
-            if (full[u]) {
-                #pragma unroll
-                for (int j = 0; j < MT_ITEMS / 4; ++j) {
-                    atomicAdd(&h[mt_digit(k4[u][j].x, shift, mask, bins)], 1u);
-                    atomicAdd(&h[mt_digit(k4[u][j].y, shift, mask, bins)], 1u);
-                    atomicAdd(&h[mt_digit(k4[u][j].z, shift, mask, bins)], 1u);
-                    atomicAdd(&h[mt_digit(k4[u][j].w, shift, mask, bins)], 1u);
-                }
-            } else if (count[u]) {
-                #pragma unroll 4
-                for (int j = 0; j < MT_ITEMS; ++j) {
-                    const uint32_t i = (uint32_t) j * MT_THREADS + tid;
-                    if (i < count[u])
-                        atomicAdd(&h[mt_digit(__ldg(keys + base[u] + i), shift, mask, bins)], 1u);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS) {
-        const uint32_t d = i / MT_GROUP, t = i % MT_GROUP;
-        if (tile0 + t < g.ntiles)
-            table[table_index(g, tile0 + t, d, bins)] = mk_smem[t * bins + d];
-    }
-}
-
-// ------------------------------------------- single sorting group: ranked tiles
-//
-// match.any costs 256 issue cycles per warp instruction on B200 whenever the lanes
-// disagree (tools/ubench_warp_ops.cu; a shuffle: 5, a private LDS + STS pair:
-// 10), so the tile placement above is bound by its 16 match.any per thread.  The
-// kernels below rank WITHOUT any warp-wide matching, the way block radix ranking
-// is classically done:
-//   - a thread owns 16 CONSECUTIVE keys of the tile (blocked arrangement) and a
-//     private column of 16-bit counters, one per digit: rank of a key among the
-//     thread's keys = counter value before the increment (plain LDS / STS);
-//   - two counters (digit d and d + NB / 2) share a 32-bit word, the words are laid
-//     out digit-major / thread-minor, so ONE packed block-wide exclusive scan of
-//     NB / 2 * 512 words gives every (digit, thread) its first slot in the sorted
-//     tile (the low halves' total is added to the high halves afterwards);
-//   - counters cost shared memory per digit AND thread, which limits a pass to
-//     6-bit digits (64 bins): more buckets are sorted least-significant digit
-//     first in ceil(bits / 6) stable passes.  Between passes an element travels as
-//     ONE 32-bit word (remaining key bits << index bits | index) as soon as that
-//     fits, else as a (key, index) pair.
-// The permutation is stable for every bucket count.
-static constexpr int RK_THREADS = 512;                     // (256-thread tiles, 4 per SM, measured no faster)
-static constexpr int RK_ITEMS = 16;
-static constexpr int RK_CTAS = 2;                          // resident CTAs per SM
-static constexpr uint32_t RK_TILE = RK_THREADS * RK_ITEMS; // 8192 keys = MT_TILE
-static_assert(RK_TILE == MT_TILE, "the tile histogram kernel is shared");
-
+/// How the elements reach a pass / leave it
 enum { RK_RAW1 = 0,   // keys = the caller's values, the only pass (-> RK_FINAL)
        RK_RAW = 1,    // keys = the caller's values, first of several passes
        RK_PAIRS = 2,  // (key, index) pairs
@@ -456,91 +374,208 @@ enum { RK_RAW1 = 0,   // keys = the caller's values, the only pass (-> RK_FINAL)
 };
 enum { RK_FINAL = 0, RK_OUT_PAIRS = 1, RK_OUT_PACKED = 2 };
 
+/// Digit of an element: keys are clamped to kmax = bucket_count - 1 where they enter
+/// (out-of-range keys must not corrupt memory), so every digit is below its `bins`.
+template <int IN> B200_DEVICE uint32_t rk_digit(uint32_t x, uint32_t shift, uint32_t mask, uint32_t kmax) {
+    if constexpr (IN == RK_RAW1)
+        return min(x, kmax);
+    else if constexpr (IN == RK_RAW)
+        return (min(x, kmax) >> shift) & mask;
+    else
+        return (x >> shift) & mask;
+}
+
+/// table[table_index(tile, d) + half] = number of keys of that half tile whose digit
+/// is d.  A CTA counts MT_GROUP consecutive half tiles into one shared-memory histogram
+/// each, so that the MT_GROUP entries of a digit are contiguous in the digit-major table
+/// (one 64-byte run instead of MT_GROUP scattered words).
+/// Dynamic shared memory: MT_GROUP * bins counters.
+template <int IN, uint32_t TILE>
+__global__ void __launch_bounds__(MT_THREADS)
+mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, const TileGeom g,
+                        uint32_t shift, uint32_t mask, uint32_t kmax, uint32_t bins,
+                        uint32_t *__restrict__ table) {
+    constexpr uint32_t HALFK = TILE / 2;
+    constexpr int V = HALFK / 4 / MT_THREADS, U = 8 / V; // 16-byte loads per half, halves per step
+    static_assert(V >= 1 && MT_GROUP % U == 0, "eight 16-byte loads in flight per thread");
+    extern __shared__ uint32_t mk_smem[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile0 = blockIdx.x * (MT_GROUP / 2);
+    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS)
+        mk_smem[i] = 0;
+    __syncthreads();
+    #pragma unroll 1
+    for (uint32_t t = 0; t < MT_GROUP; t += U) {
+        uint4 k4[U][V];
+        bool full[U];
+        uint32_t base[U], count[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            base[u] = 0;
+            count[u] = 0;
+            const uint32_t tile = tile0 + (t + u) / 2, half = (t + u) & 1;
+            if (tile < g.ntiles) {
+                uint32_t tc;
+                tile_range<TILE>(g, tile, base[u], tc);
+                base[u] += half * HALFK;
+                count[u] = tc > half * HALFK ? min(tc - half * HALFK, HALFK) : 0u;
+            }
+            full[u] = count[u] == HALFK && ((uintptr_t) (keys + base[u]) & 15) == 0;
+            if (full[u]) {
+                const uint4 *v = (const uint4 *) (keys + base[u]);
+                #pragma unroll
+                for (int j = 0; j < V; ++j)
+                    k4[u][j] = ld_stream(v + j * MT_THREADS + tid);
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t *h = mk_smem + (t + u) * bins;
+            if (full[u]) {
+                #pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    atomicAdd(&h[rk_digit<IN>(k4[u][j].x, shift, mask, kmax)], 1u);
+                    atomicAdd(&h[rk_digit<IN>(k4[u][j].y, shift, mask, kmax)], 1u);
+                    atomicAdd(&h[rk_digit<IN>(k4[u][j].z, shift, mask, kmax)], 1u);
+                    atomicAdd(&h[rk_digit<IN>(k4[u][j].w, shift, mask, kmax)], 1u);
+                }
+            } else if (count[u]) {
+                for (uint32_t i = tid; i < count[u]; i += MT_THREADS)
+                    atomicAdd(&h[rk_digit<IN>(__ldg(keys + base[u] + i), shift, mask, kmax)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS) {
+        const uint32_t d = i / MT_GROUP, t = i % MT_GROUP;
+        if (tile0 + t / 2 < g.ntiles)
+            table[table_index(g, tile0 + t / 2, d, bins) + (t & 1)] = mk_smem[t * bins + d];
+    }
+}
+
+// ------------------------------------------- single sorting group: ranked tiles
+//
+// match.any costs 256 issue cycles per warp instruction on B200 whenever the lanes
+// disagree (tools/ubench_warp_ops.cu; a shuffle: 5, a conflict-free atoms.add: 4),
+// so the kernels below rank WITHOUT any warp-wide matching, the way block radix
+// ranking is classically done -- with the counters driven by shared-memory ATOMICS:
+//   - a thread owns 16 CONSECUTIVE keys of the tile (blocked arrangement) and a
+//     private column of 16-bit counters, one per digit.  Counting is one
+//     fire-and-forget atoms.add per key on the thread's own counter (no conflicts:
+//     bank = lane; no load -> add -> store chain);
+//   - two counters (the same digit of thread t and of thread t + THREADS / 2) share a
+//     32-bit word, the words are laid out digit-major / thread-minor, so ONE packed
+//     block-wide exclusive scan of NB * THREADS / 2 words turns every counter into the
+//     first STAGING slot of its (digit, thread) pair (sorted-tile slot + the run's
+//     alignment shift, see below);
+//   - placement is one atoms.add WITH return per key: it hands out the key's slot and
+//     advances the thread's cursor in one instruction;
+//   - counters cost shared memory per digit AND thread, which limits a pass to
+//     6-bit digits (64 bins): more buckets are sorted least-significant digit
+//     first in ceil(bits / 6) stable passes.  Between passes an element travels as
+//     ONE 32-bit word (remaining key bits << index bits | index) as soon as that
+//     fits, else as a (key, index) pair.
+// The permutation is stable for every bucket count.
+static constexpr int RK_ITEMS = 16;
 static constexpr uint32_t RK_PAD = 8;  // staging slack per run (alignment)
 
-template <int BITS> constexpr uint32_t rk_stage_words() { return RK_TILE + RK_PAD * 2 * (1u << BITS); }
-template <int BITS> constexpr size_t rk_smem_bytes() {
-    // packed counters + sorted tile + per-run {shift, start, count, global start}
-    return (size_t) ((1u << BITS) * (RK_THREADS / 2) + rk_stage_words<BITS>() + 4 * 2 * (1u << BITS)) * 4;
+template <int BITS, int THREADS> constexpr uint32_t rk_stage_words() {
+    return THREADS * RK_ITEMS + RK_PAD * 2 * (1u << BITS);
+}
+template <int BITS, int THREADS> constexpr size_t rk_smem_bytes() {
+    // packed counters + sorted tile + per-run {start, global slot}
+    return (size_t) ((1u << BITS) * (THREADS / 2) + rk_stage_words<BITS, THREADS>() + 2 * (2 * (1u << BITS) + 4)) * 4;
+}
+
+struct RkArgs {
+    const uint32_t *in0, *in1, *table;
+    TileGeom geom;
+    uint32_t shift, mask, bins, width, ib, kmax, index_base;
+    uint32_t *out0, *out1;
+};
+
+/// Staging slot of run r (sorted-tile slot `ls`, first global slot at word address
+/// `gword`): 16-byte aligned staging words coincide with 16-byte aligned global
+/// addresses, consecutive runs keep RK_PAD words of slack.
+B200_DEVICE uint32_t rk_stage_pos(uint32_t ls, uint32_t r, uint32_t gword) {
+    return ((ls + RK_PAD * r + 3u) & ~3u) + (gword & 3u);
 }
 
 /// in0 / in1: keys (RAW*, PAIRS) or packed words (PACKED) / indices (PAIRS).
-/// digit = min((x >> shift) & mask, bins - 1) with x the key or the packed word.
 /// out0 / out1: permutation (FINAL), keys / indices (PAIRS), packed words (PACKED).
-/// ib: index bits of a packed word, keymask: the valid key bits, index_base: index
-/// of element 0 (the permutation holds GLOBAL indices, resources/mkperm.cuh:373-376).
+/// ib: index bits of a packed word, width: bits of this digit, index_base: index of
+/// element 0 (the permutation holds GLOBAL indices, resources/mkperm.cuh:373-376).
 ///
 /// Counters: the 16-bit counter of (digit d, thread t) lives in 32-bit word
-/// d * 256 + (t % 256), low half for t < 256, high half for t >= 256 -- so that the
-/// counter address is ONE multiply-add away from the digit, and one packed scan
-/// over the words in (digit, column) order ranks the keys of the lower and of the
-/// upper 256 threads at once.  The sorted tile therefore consists of 2 * bins runs
-/// (lower-half threads: digits 0 .. bins - 1, then the upper-half threads); the two
-/// runs of a digit are adjacent in the OUTPUT, where only the order matters.
+/// d * HALF + (t % HALF), low half for t < HALF = THREADS / 2, high half above -- the
+/// counter address is ONE multiply-add away from the digit.  The sorted tile consists
+/// of 2 * NB runs (lower-half threads: digits 0 .. NB - 1, then the upper-half
+/// threads); the two runs of a digit are adjacent in the OUTPUT, where only the order
+/// matters.
 ///
 /// Every run is staged in shared memory so that its 16-byte aligned part coincides
 /// with 16-byte aligned global addresses and leaves with ONE bulk copy shared ->
-/// global (cp.async.bulk) plus at most 3 + 3 scalar stores for its ragged ends --
-/// there is no per-element store loop.
-template <int BITS, int IN, int OUT, bool FULL>
-B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
-                         const uint32_t *__restrict__ table, const TileGeom &geom, uint64_t base,
-                         uint32_t tile_count_in,
-                         uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
-                         uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
-                         uint32_t *__restrict__ out1, uint32_t *rk_smem, uint32_t tile) {
-    constexpr uint32_t NB = 1u << BITS, WPT = NB / 2, G = WPT / 4, HALF = RK_THREADS / 2;
+/// global (cp.async.bulk) plus at most 3 + 3 scalar stores for its ragged ends, all
+/// issued by ONE thread per run -- there is no per-element store loop.
+template <int BITS, int IN, int OUT, int THREADS, bool FULL>
+B200_DEVICE void rk_tile(const RkArgs &a, uint32_t tile, uint32_t base, uint32_t tile_count_in,
+                         uint32_t ahead_tiles, uint32_t *rk_smem) {
+    constexpr uint32_t ITEMS = RK_ITEMS, TILE = THREADS * ITEMS, HALF = THREADS / 2, NWARPS = THREADS / 32;
+    constexpr uint32_t NB = 1u << BITS, WPT = NB / 2, G = WPT / 4;
     constexpr uint32_t ROTM = G < HALF / 32 ? G : HALF / 32; // distinct rotations (see below)
-    uint32_t *s_cnt = rk_smem;                              // NB * 256 packed counters
-    uint32_t *s_stage = rk_smem + NB * HALF;                // sorted tile (+ alignment slack)
-    uint32_t *s_shift = s_stage + rk_stage_words<BITS>();   // staging slot - sorted-tile slot, per run
-    uint32_t *s_pos = s_shift + 2 * NB;                     // staging slot of the run
-    uint32_t *s_len = s_pos + 2 * NB;                       // length of the run
-    uint32_t *s_gpos = s_len + 2 * NB;                      // first global slot of the run
-    __shared__ uint32_t s_warp[RK_THREADS / 32];
+    static_assert(G >= 1 && HALF % WPT == 0, "counter rows must consist of whole scan segments");
+    static_assert(2 * NB <= THREADS && NWARPS <= 32, "one thread per run");
+    uint32_t *s_cnt = rk_smem;                                     // NB * HALF packed counters
+    uint32_t *s_stage = rk_smem + NB * HALF;                       // sorted tile (+ alignment slack)
+    uint32_t *s_rstart = s_stage + rk_stage_words<BITS, THREADS>();// 2 * NB + 1 run starts (sorted-tile slots)
+    uint32_t *s_gpos = s_rstart + 2 * NB + 4;                      // first global slot of the run
+    __shared__ uint32_t s_warp[32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile_count = FULL ? RK_TILE : tile_count_in;
-    // first output slot of the tile's sorting group
-    const uint32_t group_start = (tile / geom.tpg) * geom.group_size;
-    const uint32_t first = tid * RK_ITEMS; // tile-local index of the thread's first key
+    const uint32_t tile_count = FULL ? TILE : tile_count_in;
+    const uint32_t first = tid * ITEMS; // tile-local index of the thread's first key
+    const uint32_t half = tid / HALF;
 
     #pragma unroll
     for (uint32_t j = 0; j < G; ++j)
-        ((uint4 *) s_cnt)[j * RK_THREADS + tid] = make_uint4(0, 0, 0, 0);
+        ((uint4 *) s_cnt)[j * THREADS + tid] = make_uint4(0, 0, 0, 0);
 
     // ---- load (blocked: 64 contiguous bytes per thread)
-    uint32_t key[RK_ITEMS];
-    auto load16 = [&](const uint32_t *src, uint32_t (&dst)[RK_ITEMS]) {
+    uint32_t key[ITEMS];
+    auto load = [&](const uint32_t *src, uint32_t (&dst)[ITEMS]) {
         if (FULL && ((uintptr_t) (src + base) & 15) == 0) {
-            const uint4 *v = (const uint4 *) (src + base) + tid * (RK_ITEMS / 4);
+            const uint4 *v = (const uint4 *) (src + base) + tid * (ITEMS / 4);
             #pragma unroll
-            for (int q = 0; q < RK_ITEMS / 4; ++q) {
+            for (int q = 0; q < (int) ITEMS / 4; ++q) {
                 const uint4 k4 = __ldg(v + q);
                 dst[4 * q] = k4.x; dst[4 * q + 1] = k4.y; dst[4 * q + 2] = k4.z; dst[4 * q + 3] = k4.w;
             }
         } else {
             #pragma unroll
-            for (int i = 0; i < RK_ITEMS; ++i)
+            for (int i = 0; i < (int) ITEMS; ++i)
                 dst[i] = first + i < tile_count ? __ldg(src + base + first + i) : 0u;
         }
     };
-    load16(in0, key);
+    load(a.in0, key);
     // the next tile of this (persistent) CTA will find its keys in L2
-    if (tile + ahead_tiles < geom.ntiles) {
-        uint64_t abase;
-        uint32_t acount;
-        tile_range(geom, tile + ahead_tiles, abase, acount);
-        if (first + RK_ITEMS <= acount) {
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(in0 + abase + first));
+    if (tile + ahead_tiles < a.geom.ntiles && (tid & 1) == 0) {
+        uint32_t abase, acount;
+        tile_range<TILE>(a.geom, tile + ahead_tiles, abase, acount);
+        if (first + 2 * ITEMS <= acount) { // one 128-byte line per two threads
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(a.in0 + abase + first));
             if constexpr (IN == RK_PAIRS)
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(in1 + abase + first));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(a.in1 + abase + first));
         }
     }
-    // first output slot of this tile's keys with digit (tid % bins): run tid
-    uint32_t gstart = 0;
-    if (tid < 2 * bins)
-        gstart = group_start + __ldg(table + table_index(geom, tile, tid < bins ? tid : tid - bins, bins));
+    // first output slot of run tid: digit (tid % NB) of half (tid / NB)
+    if (tid < 2 * NB) {
+        uint32_t gstart = 0;
+        if ((tid & (NB - 1)) < a.bins) {
+            const uint32_t group_start = a.geom.tpg == a.geom.ntiles ? 0u : (tile / a.geom.tpg) * a.geom.group_size;
+            gstart = group_start + __ldg(a.table + table_index(a.geom, tile, tid & (NB - 1), a.bins) + tid / NB);
+        }
+        s_gpos[tid] = gstart;
+    }
 
     // The scan below has thread t' rake the WPT consecutive words [t' * WPT, (t' + 1)
     // * WPT) with 128-bit accesses; rotating the 16-byte groups of a thread's segment
@@ -550,32 +585,35 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     // thread's column.
     const uint32_t col = tid & (HALF - 1);
     const uint32_t pcol = (col & ~(WPT - 1)) | (((((col % WPT) >> 2) + (col >> 5) % ROTM) % G) << 2) | (col & 3);
-    uint8_t *cnt_mine = (uint8_t *) s_cnt + pcol * 4 + (tid / HALF) * 2;
+    uint32_t *cnt_mine = s_cnt + pcol;
+    const uint32_t inc = 1u << (16 * half);
+    if constexpr (IN == RK_RAW1 || IN == RK_RAW) {
+        #pragma unroll
+        for (int i = 0; i < (int) ITEMS; ++i)
+            key[i] = min(key[i], a.kmax);
+    }
     auto digit = [&](uint32_t x) -> uint32_t {
         if constexpr (IN == RK_RAW1)
-            return min(x, bins - 1);
+            return x;
         else
-            return min((x >> shift) & mask, bins - 1);
+            return (x >> a.shift) & a.mask;
     };
     __syncthreads();
 
-    // ---- rank among the thread's own keys (4 bits each)
-    uint32_t lr[2] = { 0, 0 };
+    // ---- count: one fire-and-forget atomic per key on the thread's own counters
     #pragma unroll
-    for (int i = 0; i < RK_ITEMS; ++i) {
-        if (FULL || first + i < tile_count) {
-            uint16_t *c = (uint16_t *) (cnt_mine + digit(key[i]) * (HALF * 4));
-            const uint32_t v = *c;
-            *c = (uint16_t) (v + 1);
-            lr[i / 8] |= v << (4 * (i & 7));
-        }
+    for (int i = 0; i < (int) ITEMS; ++i) {
+        if (FULL || first + i < tile_count)
+            atomicAdd(cnt_mine + digit(key[i]) * HALF, inc);
     }
     __syncthreads();
 
     // ---- packed exclusive scan of the counters (digit-major, column-minor)
+    const uint32_t rot = (tid * G / 8) % ROTM;
+    uint4 *seg = (uint4 *) s_cnt + tid * G;
+    const uint32_t row = tid * WPT / HALF; // digit of this thread's segment
+    uint32_t run;
     {
-        const uint32_t rot = (tid * G / 8) % ROTM;
-        uint4 *seg = (uint4 *) s_cnt + tid * G;
         uint32_t mine = 0;
         #pragma unroll
         for (uint32_t j = 0; j < G; ++j) {
@@ -592,14 +630,32 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
         if (lane == 31)
             s_warp[warp] = incl;
         __syncthreads();
-        uint32_t run = incl - mine, total = 0;
-        #pragma unroll
-        for (int w = 0; w < RK_THREADS / 32; ++w) {
-            const uint32_t t = s_warp[w];
-            run += (uint32_t) w < warp ? t : 0u;
-            total += t;
-        }
+        const uint32_t wt = lane < NWARPS ? s_warp[lane] : 0u;
+        const uint32_t total = __reduce_add_sync(FULL_MASK, wt);
+        run = incl - mine + __reduce_add_sync(FULL_MASK, lane < warp ? wt : 0u);
         run += total << 16; // the upper-half threads' keys come after all lower-half ones
+        // run starts: the segment that begins a digit's row of HALF words
+        if ((tid * WPT) % HALF == 0) {
+            s_rstart[row] = run & 0xffffu;
+            s_rstart[NB + row] = run >> 16;
+        }
+        if (tid == 0)
+            s_rstart[2 * NB] = tile_count;
+    }
+    uint32_t idx[IN == RK_PAIRS ? ITEMS : 1];
+    if constexpr (IN == RK_PAIRS)
+        load(a.in1, idx);
+    // the bulk copies of the CTA's previous tile may still be reading the staging area
+    if (tid < 2 * NB)
+        bulk_wait_read<0>();
+    __syncthreads();
+
+    // ---- second half of the scan: counter = first STAGING slot of its (digit, thread)
+    {
+        const uint32_t gword = (uint32_t) ((uintptr_t) a.out0 >> 2);
+        const uint32_t lo = s_rstart[row], hi = s_rstart[NB + row];
+        run += (rk_stage_pos(lo, row, gword + s_gpos[row]) - lo) |
+               ((rk_stage_pos(hi, NB + row, gword + s_gpos[NB + row]) - hi) << 16);
         #pragma unroll
         for (uint32_t j = 0; j < G; ++j) {
             uint4 v = seg[(j + rot) % G], o;
@@ -612,164 +668,140 @@ B200_DEVICE void rk_tile(const uint32_t *__restrict__ in0, const uint32_t *__res
     }
     __syncthreads();
 
-    // ---- where every run is staged and where it goes.  Run r < bins: digit r of the
-    // lower-half threads; run bins + d: digit d of the upper-half threads.
-    if (tid < 2 * bins) {
-        auto run_start = [&](uint32_t r) -> uint32_t { // sorted-tile slot of the run's first key
-            if (r >= 2 * bins)
-                return tile_count;
-            const uint32_t d = r < bins ? r : r - bins;
-            return ((const uint16_t *) s_cnt)[d * (HALF * 2) + (r < bins ? 0 : 1)];
-        };
-        const uint32_t ls = run_start(tid), le = run_start(tid + 1);
-        uint32_t gpos = gstart;
-        if (tid >= bins) // after the lower-half threads' keys of the same digit
-            gpos += run_start(tid - bins + 1) - run_start(tid - bins);
-        const uint32_t galign = (uint32_t) (((uintptr_t) (out0 + gpos)) >> 2) & 3u;
-        const uint32_t pos = ((ls + RK_PAD * tid + 3u) & ~3u) + galign;
-        s_shift[tid] = pos - ls;
-        s_pos[tid] = pos;
-        s_len[tid] = le - ls;
-        s_gpos[tid] = gpos;
-    }
-    uint32_t idx[IN == RK_PAIRS ? RK_ITEMS : 1];
-    if constexpr (IN == RK_PAIRS)
-        load16(in1, idx);
-    // the bulk copies of the CTA's previous tile may still be reading the staging area
-    if (lane == 0)
-        bulk_wait_read<0>();
-    __syncthreads();
-
-    // ---- sort into the staging area (values are final: what is stored to global)
-    uint32_t slot2[OUT == RK_OUT_PAIRS ? RK_ITEMS / 2 : 1] = {};
-    const uint32_t idxmask = ib >= 32 ? 0xffffffffu : (1u << ib) - 1u;
-    const uint32_t *shift_mine = s_shift + (tid / HALF) * bins;
+    // ---- place: the atomic returns the key's slot and advances the thread's cursor
+    uint32_t slot2[OUT == RK_OUT_PAIRS ? ITEMS / 2 : 1] = {};
+    const uint32_t idxmask = a.ib >= 32 ? 0xffffffffu : (1u << a.ib) - 1u;
+    const uint32_t hshift = 16 * half;
+    // (batches of eight: the atomics of a batch are in flight together, their results
+    // are consumed by the stores that follow)
     #pragma unroll
-    for (int i = 0; i < RK_ITEMS; ++i) {
-        if (FULL || first + i < tile_count) {
-            const uint32_t d = digit(key[i]);
-            const uint32_t sl = *(const uint16_t *) (cnt_mine + d * (HALF * 4)) +
-                                ((lr[i / 8] >> (4 * (i & 7))) & 15u) + shift_mine[d];
-            const uint32_t w = key[i];
-            uint32_t v;
-            if constexpr (IN == RK_RAW1) {
-                v = index_base + (uint32_t) base + first + i;
-            } else if constexpr (IN == RK_PACKED) {
-                v = OUT == RK_FINAL ? w & idxmask : ((w >> (ib + BITS)) << ib) | (w & idxmask);
-            } else {
-                const uint32_t ix = IN == RK_PAIRS ? idx[i] : index_base + (uint32_t) base + first + i;
-                if constexpr (OUT == RK_FINAL)
-                    v = ix;
-                else if constexpr (OUT == RK_OUT_PACKED)
-                    v = (((w & keymask) >> (shift + BITS)) << ib) | ix;
-                else
-                    v = w; // keys first, indices in a second round
+    for (int i0 = 0; i0 < (int) ITEMS; i0 += 8) {
+        uint32_t sl[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j;
+            sl[j] = 0;
+            if (FULL || first + i < tile_count)
+                sl[j] = (atomicAdd(cnt_mine + digit(key[i]) * HALF, inc) >> hshift) & 0xffffu;
+        }
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j;
+            if (FULL || first + i < tile_count) {
+                const uint32_t w = key[i];
+                uint32_t v;
+                if constexpr (IN == RK_RAW1) {
+                    v = a.index_base + base + first + i;
+                } else if constexpr (IN == RK_PACKED) {
+                    v = OUT == RK_FINAL ? w & idxmask : ((w >> (a.ib + a.width)) << a.ib) | (w & idxmask);
+                } else {
+                    const uint32_t ix = IN == RK_PAIRS ? idx[i] : a.index_base + base + first + i;
+                    if constexpr (OUT == RK_FINAL)
+                        v = ix;
+                    else if constexpr (OUT == RK_OUT_PACKED)
+                        v = ((w >> (a.shift + a.width)) << a.ib) | ix;
+                    else
+                        v = w; // keys first, indices in a second round
+                }
+                s_stage[sl[j]] = v;
+                if constexpr (OUT == RK_OUT_PAIRS)
+                    slot2[i / 2] |= sl[j] << (16 * (i & 1));
             }
-            s_stage[sl] = v;
-            if constexpr (OUT == RK_OUT_PAIRS)
-                slot2[i / 2] |= sl << (16 * (i & 1));
         }
     }
 
-    // a warp writes runs warp, warp + 16, ...
+    // thread r writes run r
     auto write_runs = [&](uint32_t *out) {
         fence_proxy_async();
         __syncthreads();
-        for (uint32_t r = warp; r < 2 * bins; r += RK_THREADS / 32) {
-            const uint32_t len = s_len[r];
-            if (len == 0)
-                continue;
-            const uint32_t *src = s_stage + s_pos[r];
-            uint32_t *dst = out + s_gpos[r];
-            if (len < 64) { // short run: one or two coalesced store instructions
-                for (uint32_t i = lane; i < len; i += 32)
+        if (tid < 2 * NB) {
+            const uint32_t ls = s_rstart[tid], len = s_rstart[tid + 1] - ls;
+            if (len) {
+                const uint32_t g = s_gpos[tid];
+                // (out0 and out1 are allocations of the same alignment class)
+                const uint32_t *src = s_stage + rk_stage_pos(ls, tid, (uint32_t) ((uintptr_t) a.out0 >> 2) + g);
+                uint32_t *dst = out + g;
+                const uint32_t head = min((4u - ((uint32_t) ((uintptr_t) dst >> 2) & 3u)) & 3u, len);
+                const uint32_t mid = (len - head) & ~3u;
+                if (mid)
+                    bulk_s2g(dst + head, src + head, mid * 4);
+                for (uint32_t i = 0; i < head; ++i)
                     dst[i] = src[i];
-                continue;
+                for (uint32_t i = head + mid; i < len; ++i)
+                    dst[i] = src[i];
             }
-            const uint32_t head = (4u - (s_pos[r] & 3u)) & 3u;
-            const uint32_t mid = (len - head) & ~3u, tail = len - head - mid;
-            if (lane == 0) {
-                bulk_s2g(dst + head, src + head, mid * 4);
-                bulk_commit();
-            }
-            if (lane >= 1 && lane - 1 < head)
-                dst[lane - 1] = src[lane - 1];
-            else if (lane >= 4 && lane - 4 < tail)
-                dst[head + mid + lane - 4] = src[head + mid + lane - 4];
+            bulk_commit();
         }
     };
-    write_runs(out0);
+    write_runs(a.out0);
     if constexpr (OUT == RK_OUT_PAIRS) {
         // second round: the indices travel through the same staging area
-        if (lane == 0)
+        if (tid < 2 * NB)
             bulk_wait_read<0>();
         __syncthreads();
         #pragma unroll
-        for (int i = 0; i < RK_ITEMS; ++i) {
+        for (int i = 0; i < (int) ITEMS; ++i) {
             if (FULL || first + i < tile_count)
                 s_stage[(slot2[i / 2] >> (16 * (i & 1))) & 0xffffu] =
-                    IN == RK_PAIRS ? idx[i] : index_base + (uint32_t) base + first + i;
+                    IN == RK_PAIRS ? idx[i] : a.index_base + base + first + i;
         }
-        write_runs(out1);
+        write_runs(a.out1);
     }
 }
 
-template <int BITS, int IN, int OUT>
-__global__ void __launch_bounds__(RK_THREADS, RK_CTAS)
-mkperm_rank_place_kernel(const uint32_t *__restrict__ in0, const uint32_t *__restrict__ in1,
-                         const uint32_t *__restrict__ table, const TileGeom geom,
-                         uint32_t shift, uint32_t mask, uint32_t bins, uint32_t ib, uint32_t keymask,
-                         uint32_t ahead_tiles, uint32_t index_base, uint32_t *__restrict__ out0,
-                         uint32_t *__restrict__ out1) {
+template <int THREADS> constexpr int rk_ctas() { return 1024 / THREADS; } // resident CTAs per SM (64 registers)
+
+template <int BITS, int IN, int OUT, int THREADS>
+__global__ void __launch_bounds__(THREADS, rk_ctas<THREADS>())
+mkperm_rank_place_kernel(const RkArgs a, uint32_t ahead_tiles) {
     constexpr bool TWO = IN == RK_RAW || IN == RK_PAIRS;
+    constexpr uint32_t TILE = THREADS * RK_ITEMS;
     static_assert(BITS >= 3 && BITS <= 6, "3..6-bit digits");
     static_assert(TWO ? OUT != RK_FINAL || IN == RK_PAIRS : OUT != RK_OUT_PAIRS, "unsupported combination");
     extern __shared__ __align__(16) uint32_t rk_smem[];
-    auto one_tile = [&](uint32_t tile) {
-        uint64_t base;
-        uint32_t count;
-        tile_range(geom, tile, base, count);
-        if (count == RK_TILE)
-            rk_tile<BITS, IN, OUT, true>(in0, in1, table, geom, base, count, shift, mask, bins, ib, keymask,
-                                         ahead_tiles, index_base, out0, out1, rk_smem, tile);
+    // persistent CTAs: the bulk stores of a tile drain while the next one is loaded,
+    // counted and scanned
+    for (uint32_t tile = blockIdx.x; tile < a.geom.ntiles; tile += gridDim.x) {
+        uint32_t base, count;
+        tile_range<TILE>(a.geom, tile, base, count);
+        if (count == TILE)
+            rk_tile<BITS, IN, OUT, THREADS, true>(a, tile, base, count, ahead_tiles, rk_smem);
         else if (count) // block-uniform
-            rk_tile<BITS, IN, OUT, false>(in0, in1, table, geom, base, count, shift, mask, bins, ib, keymask,
-                                          ahead_tiles, index_base, out0, out1, rk_smem, tile);
-    };
-    if constexpr (IN == RK_RAW1) {
-        // persistent CTAs: the bulk stores of a tile drain while the next one is loaded and
-        // counted (154 vs 165 us per 2^26 keys; the variants that carry more state spill
-        // in the loop and are launched one tile per CTA)
-        for (uint32_t tile = blockIdx.x; tile < geom.ntiles; tile += gridDim.x)
-            one_tile(tile);
-    } else {
-        one_tile(blockIdx.x);
+            rk_tile<BITS, IN, OUT, THREADS, false>(a, tile, base, count, ahead_tiles, rk_smem);
     }
     // the staging area must outlive the bulk copies that read it
-    if ((threadIdx.x & 31) == 0)
-        bulk_wait_read<0>();
+    bulk_wait_read<0>();
 }
 
-struct RkArgs {
-    const uint32_t *in0, *in1, *table;
-    TileGeom geom;
-    uint32_t shift, mask, bins, ib, keymask, index_base;
-    uint32_t *out0, *out1;
-};
+/// Keys per tile: 8192 (512 threads) unless B200_MKPERM_TILE=4096 (development switch)
+static uint32_t rk_tile_keys() {
+    static int tile = -1;
+    if (tile < 0) {
+        const char *e = getenv("B200_MKPERM_TILE");
+        tile = e && atoi(e) == 4096 ? 4096 : 8192;
+    }
+    return (uint32_t) tile;
+}
 
-template <int BITS, int IN, int OUT>
-static cudaError_t rk_launch_one(cudaStream_t stream, const RkArgs &a) {
-    constexpr size_t smem = rk_smem_bytes<BITS>();
-    auto kernel = mkperm_rank_place_kernel<BITS, IN, OUT>;
+template <int BITS, int IN, int OUT, int THREADS>
+static cudaError_t rk_launch_cfg(cudaStream_t stream, const RkArgs &a) {
+    constexpr size_t smem = rk_smem_bytes<BITS, THREADS>();
+    auto kernel = mkperm_rank_place_kernel<BITS, IN, OUT, THREADS>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess)
         return err;
-    const uint32_t resident = (uint32_t) (RK_CTAS * sm_count());
-    const uint32_t grid = IN == RK_RAW1 ? std::min<uint32_t>(a.geom.ntiles, resident) : a.geom.ntiles;
-    kernel<<<grid, RK_THREADS, smem, stream>>>(a.in0, a.in1, a.table, a.geom, a.shift, a.mask,
-                                               a.bins, a.ib, a.keymask, resident, a.index_base, a.out0, a.out1);
+    const uint32_t per_sm = std::min<uint32_t>(rk_ctas<THREADS>(), (uint32_t) ((227 * 1024) / (smem + 1024)));
+    const uint32_t grid = std::min<uint32_t>(a.geom.ntiles, per_sm * (uint32_t) sm_count());
+    kernel<<<grid, THREADS, smem, stream>>>(a, grid);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int BITS, int IN, int OUT>
+static cudaError_t rk_launch_one(cudaStream_t stream, const RkArgs &a) {
+    if (rk_tile_keys() == 4096)
+        return rk_launch_cfg<BITS, IN, OUT, 256>(stream, a);
+    return rk_launch_cfg<BITS, IN, OUT, 512>(stream, a);
 }
 
 template <int BITS>
@@ -795,6 +827,27 @@ static cudaError_t rk_launch(cudaStream_t stream, int bits, int in, int out, con
         case 6: return rk_launch_bits<6>(stream, in, out, a);
     }
     return cudaErrorInvalidValue;
+}
+
+template <uint32_t TILE>
+static void tile_hist_launch(cudaStream_t stream, int form, const uint32_t *in0, const RkArgs &a) {
+    const uint32_t grid = (uint32_t) ceil_div(a.geom.ntiles, MT_GROUP / 2);
+    const size_t smem = (size_t) MT_GROUP * a.bins * 4;
+    uint32_t *table = const_cast<uint32_t *>(a.table);
+    switch (form) {
+        case RK_RAW1:
+            mkperm_tile_hist_kernel<RK_RAW1, TILE><<<grid, MT_THREADS, smem, stream>>>(
+                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, table);
+            break;
+        case RK_RAW:
+            mkperm_tile_hist_kernel<RK_RAW, TILE><<<grid, MT_THREADS, smem, stream>>>(
+                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, table);
+            break;
+        default:
+            mkperm_tile_hist_kernel<RK_PACKED, TILE><<<grid, MT_THREADS, smem, stream>>>(
+                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, table);
+    }
+    count_launch();
 }
 
 static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t size,
@@ -852,13 +905,13 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
     TileGeom geom{};
     geom.size = size;
     geom.group_size = group_size;
-    geom.tpg = (uint32_t) ceil_div(group_size, RK_TILE);
+    const uint32_t tile_keys = rk_tile_keys();
+    geom.tpg = (uint32_t) ceil_div(group_size, tile_keys);
     const uint64_t ngroups = ceil_div(size, group_size);
     if (ngroups * geom.tpg > 0x7fffffffull)
         return fail(B200_ERR_INVALID, "jit_block_mkperm(): too many tiles!");
     geom.ntiles = (uint32_t) (ngroups * geom.tpg);
     const uint32_t ntiles = geom.ntiles;
-    const uint32_t keymask = total_bits >= 32 ? 0xffffffffu : (1u << total_bits) - 1u;
 
     // digit widths: as even as possible, wider digits last (a wide digit costs
     // counters and runs; the last passes move one word per element, not two)
@@ -869,7 +922,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
         sh += width[p];
     }
 
-    const uint64_t max_counts = (uint64_t) 64 * ntiles;
+    const uint64_t max_counts = (uint64_t) 64 * 2 * ntiles;
     uint32_t *table = (uint32_t *) temp_alloc(max_counts * 4, stream);
     uint32_t *tmp[4] = { nullptr, nullptr, nullptr, nullptr };
     auto cleanup = [&]() {
@@ -891,7 +944,8 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
         a.table = table;
         a.geom = geom;
         a.ib = ib;
-        a.keymask = keymask;
+        a.kmax = bucket_count - 1;
+        a.width = width[p];
         a.index_base = index_base;
         if (form == RK_RAW1) {
             a.shift = 0;
@@ -924,14 +978,14 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
             a.out1 = tmp[set + 1];
         }
 
-        const uint64_t ncounts = (uint64_t) a.bins * ntiles;
-        mkperm_tile_hist_kernel<<<(uint32_t) ceil_div(ntiles, MT_GROUP), MT_THREADS,
-                                  (size_t) MT_GROUP * a.bins * 4, stream>>>(
-            in0, geom, a.shift, a.mask, a.bins, table);
-        count_launch();
-        // one exclusive scan per group over its [digit][tile] counts
+        const uint64_t ncounts = (uint64_t) a.bins * 2 * ntiles;
+        if (tile_keys == 4096)
+            tile_hist_launch<4096>(stream, form, in0, a);
+        else
+            tile_hist_launch<8192>(stream, form, in0, a);
+        // one exclusive scan per group over its [digit][tile][half] counts
         int rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts,
-                                          (uint64_t) a.bins * geom.tpg, 1, 0, table, table);
+                                          (uint64_t) a.bins * geom.tpg * 2, 1, 0, table, table);
         if (rc) {
             cleanup();
             return rc;
@@ -943,7 +997,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
                 cleanup();
                 return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
             }
-            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(table, ntiles, bucket_count, size, records);
+            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(table, 2 * (uint64_t) ntiles, bucket_count, size, records);
             count_launch();
             cudaError_t err = cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
                                               cudaMemcpyDeviceToHost, stream);
@@ -1067,7 +1121,7 @@ static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
 
     // one sorting group (vectorised method dispatch) or groups of at least half a tile:
     // ranked tiles.  Smaller groups would leave the tiles mostly empty: row kernels.
-    if (ngroups == 1 || block_size >= RK_TILE / 2) {
+    if (ngroups == 1 || block_size >= rk_tile_keys() / 2) {
         rc = mkperm_ranked(stream, values, size, block_size, bucket_count, perm,
                            ngroups == 1 ? offsets : nullptr);
         if (rc)

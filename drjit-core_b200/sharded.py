@@ -80,8 +80,17 @@ def shard_bounds(total, world, rank):
 
 
 class Sharded:
-    def __init__(self, group=None, device=None, local_ops=None, seeded_min_tiles=64):
+    """exchange="peer": the collectives are ONE C-ABI call per rank (b200_sharded_*):
+    totals travel through peer-mapped mailboxes over NVLink, no NCCL call and no
+    allocation on the data path (csrc/sharded.cu).  exchange="nccl": the local passes
+    are C-ABI calls, the totals are gathered with torch.distributed (also what the
+    gloo tests on CPU exercise with a stand-in for the local passes).  "auto": peer
+    mailboxes on CUDA when the IPC mapping succeeds on every rank, else nccl."""
+
+    def __init__(self, group=None, device=None, local_ops=None, seeded_min_tiles=64,
+                 exchange="auto"):
         self.seeded_min_tiles = seeded_min_tiles
+        self.peer = None
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -89,6 +98,41 @@ class Sharded:
             torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available()
             else torch.device("cpu"))
         self.ops = local_ops if local_ops is not None else CudaLocalOps()
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError(f"exchange must be auto, peer or nccl (got {exchange!r})")
+        if exchange != "nccl" and local_ops is None and self.device.type == "cuda":
+            self._connect_peers(required=(exchange == "peer"))
+
+    def _connect_peers(self, required):
+        from . import ShardedContext
+
+        def gather(handle):
+            if self.world == 1:
+                return [handle]
+            out = [None] * self.world
+            dist.all_gather_object(out, handle, group=self.group)
+            return out
+
+        err = None
+        try:
+            self.peer = ShardedContext(self.rank, self.world, gather)
+        except (RuntimeError, AssertionError) as e:
+            err = e
+        # every rank must take the same path
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if self.peer is not None:
+                self.peer.close()
+                self.peer = None
+            if required:
+                raise RuntimeError(f"sharded: peer mailboxes could not be mapped on every rank ({err})")
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def _bytes(self, n):
         return torch.zeros(n, dtype=torch.uint8, device=self.device)
@@ -106,6 +150,9 @@ class Sharded:
     def reduce(self, vt, op, local_in, local_size, out):
         """Whole-array reduction of the global array; every rank receives the
         result in `out` (device scalar of type vt)."""
+        if self.peer is not None:
+            self.peer.reduce(vt, op, local_in, local_size, out)
+            return
         tsize = TYPE_SIZE[vt]
         partial = self._bytes(tsize)
         if local_size > 0:
@@ -128,6 +175,10 @@ class Sharded:
         if vt == VarType.Float16:
             raise RuntimeError("sharded prefix_reduce(): float16 is not supported "
                                "(per-shard totals would be rounded to half)")
+        if (self.peer is not None and local_in.data_ptr() % 16 == 0 and local_out.data_ptr() % 16 == 0):
+            # (alignment is a property of the allocation: the same on every rank)
+            self.peer.prefix_reduce(vt, op, local_size, exclusive, reverse, local_in, local_out)
+            return
         tsize = TYPE_SIZE[vt]
         total = self._bytes(tsize)
         # large shard: the reduce pass also leaves one sum per scan tile
@@ -164,6 +215,11 @@ class Sharded:
         rank).  With want_offsets also returns this rank's exclusive offset per
         bucket among the ranks (counts of lower ranks), which together with the
         exclusive scan of the global counts gives its global output slots."""
+        if self.peer is not None and bucket_count <= 65536:
+            glob = torch.empty(bucket_count, dtype=torch.int32, device=self.device)
+            before = torch.empty(bucket_count, dtype=torch.int32, device=self.device) if want_offsets else None
+            self.peer.histogram(local_values, local_size, bucket_count, glob, before)
+            return (glob, before) if want_offsets else glob
         local = torch.zeros(bucket_count, dtype=torch.int32, device=self.device)
         if local_size > 0:
             self.ops.histogram(local_values, local_size, bucket_count, local)

@@ -280,6 +280,51 @@ B200_API int b200_scatter_reduce_packet(void *stream, int vt, int op, int mode, 
                                         const void *const *values, uint32_t width,
                                         const uint32_t *index, const uint8_t *mask, uint64_t n);
 
+/* --------------------------------------------------------------- multi-GPU */
+
+/* Large reductions, whole-array prefix reductions and the mkperm histogram sharded
+ * over the GPUs of one box (BASELINE.json north_star; the reference has no
+ * multi-GPU code on this path).  One process per GPU; rank r owns a contiguous
+ * shard.  The W ranks exchange their totals through PEER-MAPPED MAILBOXES over
+ * NVLink -- no communication-library call on the data path:
+ *   b200_sharded_create    allocates this rank's mailbox (on the current device);
+ *   b200_sharded_export    writes its CUDA IPC handle (b200_sharded_handle_bytes());
+ *   b200_sharded_connect   maps the mailboxes of all ranks: `handles` holds the W
+ *                          exported handles in rank order (gathered by the host
+ *                          program over any channel, e.g. torch.distributed).
+ * Collectives (every rank calls them in the same order, each rank on ONE stream):
+ * all are asynchronous; a rank that waits more than 20 s for a peer gives up and
+ * the next call on the context fails. */
+typedef struct B200Sharded B200Sharded;
+B200_API int b200_sharded_create(int rank, int world, B200Sharded **ctx);
+B200_API int b200_sharded_handle_bytes(void);
+B200_API int b200_sharded_export(B200Sharded *ctx, void *handle);
+B200_API int b200_sharded_connect(B200Sharded *ctx, const void *handles);
+B200_API int b200_sharded_destroy(B200Sharded *ctx);
+
+/* Reduction of the global array; every rank receives the result in *out (device).
+ * The W partials are combined in rank order on every rank: bit-exact for integers,
+ * one fixed order for floating point. */
+B200_API int b200_sharded_reduce(B200Sharded *ctx, void *stream, int vt, int op, const void *in,
+                                 uint64_t local_size, void *out);
+
+/* Prefix reduction of the global array (block_size == global size); rank r's shard
+ * of the result goes to `out`.  16-byte aligned shards of fewer than 2^32 - 2^14
+ * elements; no float16.  Three launches per rank: tile sums of the shard, one CTA
+ * that exchanges the shard totals and turns the tile sums into tile prefixes, the
+ * seeded streaming scan (b200_prefix_reduce_seeded). */
+B200_API int b200_sharded_prefix_reduce(B200Sharded *ctx, void *stream, int vt, int op,
+                                        uint64_t local_size, int exclusive, int reverse,
+                                        const void *in, void *out);
+
+/* Global bucket counts of mkperm keys (phase 1 of jit_block_mkperm over the sharded
+ * array): hist[bucket_count] on every rank; `before` (may be NULL) receives the
+ * counts of the ranks in front of this one, i.e. this rank's first output slot
+ * inside every bucket.  bucket_count <= 65536. */
+B200_API int b200_sharded_histogram(B200Sharded *ctx, void *stream, const uint32_t *values,
+                                    uint64_t local_size, uint32_t bucket_count, uint32_t *hist,
+                                    uint32_t *before);
+
 /* --------------------------------------------------------------- telemetry */
 
 /* Number of kernels this library has launched since load (all threads). */

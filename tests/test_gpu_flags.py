@@ -36,7 +36,11 @@ def test_kernel_history(dr):
     K = dr.KernelType
     for t in (K.BlockReduce, K.BlockPrefixReduce, K.Dot, K.Compress, K.MkPerm, K.Memset):
         assert t in types, (t, types)
-    assert all(h[1] == n and h[2] >= 0.0 for h in hist)
+    # (primitives that call other primitives -- mkperm scans its count table -- add
+    # entries of their own, as in the reference)
+    assert all(h[2] >= 0.0 for h in hist)
+    for t in (K.BlockReduce, K.Dot, K.Compress, K.MkPerm, K.Memset):
+        assert any(h[0] == t and h[1] == n for h in hist), t
     assert dr.jit_kernel_history() == []  # reading clears
     dr.jit_block_reduce(CUDA, VT["u32"], OP["add"], n, 1024, x, out)
     assert dr.jit_kernel_history() == []  # flag off: nothing recorded
@@ -89,7 +93,7 @@ def test_library_stream_orders_with_the_null_stream(dr):
         x = torch.randint(0, 1 << 20, (n,), dtype=torch.int32, device="cuda")  # stream 0
         out = torch.zeros(4, dtype=torch.int32, device="cuda")
         dr.jit_block_reduce(CUDA, VT["u32"], OP["add"], n, n, x, out, stream=lib_stream)
-        got = int(out[0].item())  # stream 0 again, no explicit synchronisation
+        got = int(out[0].item()) & 0xFFFFFFFF  # stream 0 again, no explicit synchronisation
         assert got == int(x.sum(dtype=torch.int64).item()) & 0xFFFFFFFF
 
 

@@ -96,6 +96,17 @@ def main():
         h = torch.empty(B, device="cuda", dtype=torch.int32)
         ms = timeit(lambda: dr.mkperm_histogram(k, n2, B, h), iters=5)
         report(f"histogram B={B}", ms, 4 * n2)
+    if on("mkperm"):
+        # skewed callee ids: one dominant bucket (what vectorised dispatch often sees)
+        B = 16
+        offs = torch.zeros(4 * B + 1, dtype=torch.int32).pin_memory()
+        k = torch.zeros(n2, device="cuda", dtype=torch.int32)
+        ms = timeit(lambda: dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, offs), iters=5)
+        report("mkperm B=16 all keys equal", ms, 8 * n2)
+        k = torch.where(torch.rand(n2, device="cuda") < 0.9, 3, torch.randint(0, B, (n2,), device="cuda")).to(torch.int32)
+        ms = timeit(lambda: dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, offs), iters=5)
+        report("mkperm B=16 90% one bucket", ms, 8 * n2)
+        del k
 
     if not on("scatter"):
         return
