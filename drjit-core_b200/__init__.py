@@ -111,6 +111,9 @@ def lib():
         L.b200_scatter_reduce.argtypes = [vp, i, i, i, vp, vp, vp, vp, u64]
         L.b200_scatter_inc.argtypes = [vp, vp, vp, vp, vp, u64]
         L.b200_scatter_reduce_packet.argtypes = [vp, i, i, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
+        L.b200_scatter_reduce_idx.argtypes = [vp, i, i, i, vp, vp, vp, i, vp, u64]
+        L.b200_scatter_packet.argtypes = [vp, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
+        L.b200_gather_packet.argtypes = [vp, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
         L.b200_sharded_create.argtypes = [i, i, ctypes.POINTER(vp)]
         L.b200_sharded_export.argtypes = [vp, vp]
         L.b200_sharded_connect.argtypes = [vp, vp]
@@ -388,6 +391,30 @@ def scatter_reduce_packet(vt, op, target, values, index, mask, n, mode=ReduceMod
     ptrs = (ctypes.c_void_p * len(values))(*[_ptr(v) for v in values])
     _check(lib().b200_scatter_reduce_packet(_stream(stream), vt, op, mode, _ptr(target), ptrs,
                                             len(values), _ptr(index), _ptr(mask), n))
+
+
+def scatter_reduce_idx(vt, op, target, value, index, index_vt, mask, n, mode=ReduceMode.Auto,
+                       stream=None):
+    """scatter_reduce with an index array of type index_vt (Int32 / UInt32 / Int64 /
+    UInt64) and with op == Identity (plain scatter) -- jitc_var_scatter, src/op.cpp:2899-3086."""
+    _check(lib().b200_scatter_reduce_idx(_stream(stream), vt, op, mode, _ptr(target), _ptr(value),
+                                         _ptr(index), index_vt, _ptr(mask), n))
+
+
+def scatter_packet(vt, target, values, index, mask, n, stream=None):
+    """target[index[i] * W + k] = values[k][i] (jit_var_scatter_packet without a
+    reduction, src/cuda_packet.cpp:329-443)."""
+    ptrs = (ctypes.c_void_p * len(values))(*[_ptr(v) for v in values])
+    _check(lib().b200_scatter_packet(_stream(stream), vt, _ptr(target), ptrs, len(values),
+                                     _ptr(index), _ptr(mask), n))
+
+
+def gather_packet(vt, source, outs, index, mask, n, stream=None):
+    """outs[k][i] = mask[i] ? source[index[i] * W + k] : 0 (jit_var_gather_packet,
+    src/cuda_packet.cpp:18-166)."""
+    ptrs = (ctypes.c_void_p * len(outs))(*[_ptr(v) for v in outs])
+    _check(lib().b200_gather_packet(_stream(stream), vt, _ptr(source), ptrs, len(outs),
+                                    _ptr(index), _ptr(mask), n))
 
 
 def jit_can_scatter_reduce(backend, vt, op):

@@ -284,6 +284,73 @@ mkperm_offsets_kernel(const uint32_t *__restrict__ starts, uint64_t stride, uint
         records[4 * (size_t) bins] = total;
 }
 
+/// The records of mkperm_offsets_kernel re-ordered by bucket size, largest first (ties:
+/// ascending bucket id) -- the order jitc_var_call_reduce launches the callees in
+/// (src/call.cpp:1346-1352 sorts on the host after the event wait).  One CTA: bitonic
+/// sort of 64-bit keys {size, ~record index} in shared memory (up to RS_SMEM records) or
+/// in `scratch` (next_pow2(bins) keys) beyond that.
+static constexpr uint32_t RS_SMEM = 4096;
+__global__ void __launch_bounds__(1024)
+mkperm_sort_records_kernel(const uint32_t *__restrict__ records, uint32_t bins,
+                           uint32_t *__restrict__ sorted, unsigned long long *__restrict__ scratch) {
+    __shared__ unsigned long long s_keys[RS_SMEM];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t count = records[4 * (size_t) bins];
+    uint32_t padded = 1;
+    while (padded < count)
+        padded <<= 1;
+    unsigned long long *keys = padded <= RS_SMEM ? s_keys : scratch;
+    for (uint32_t i = tid; i < padded; i += 1024)
+        keys[i] = i < count ? ((unsigned long long) records[4 * (size_t) i + 2] << 32) | (0xffffffffu - i) : 0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= padded; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < padded / 2; t += 1024) {
+                // the t-th pair of this step: i has bit j clear
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                const unsigned long long a = keys[i], b = keys[p];
+                const bool descending = (i & k) == 0;
+                if (descending ? a < b : a > b) {
+                    keys[i] = b;
+                    keys[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < count; i += 1024) {
+        const uint32_t src = 0xffffffffu - (uint32_t) keys[i];
+        ((uint4 *) sorted)[i] = ((const uint4 *) records)[src];
+    }
+    if (tid == 0)
+        sorted[4 * (size_t) bins] = count;
+}
+
+/// Copy the records (4 * bins + 1 words, device) into the caller's host-accessible
+/// `offsets`; by_size: ordered by bucket size first.
+static int deliver_records(cudaStream_t stream, const uint32_t *records, uint32_t bins, uint32_t *offsets,
+                           bool by_size) {
+    const size_t words = (size_t) bins * 4 + 1;
+    if (!by_size)
+        return cuda_fail(cudaMemcpyAsync(offsets, records, words * 4, cudaMemcpyDeviceToHost, stream),
+                         "cudaMemcpyAsync(offsets)");
+    uint32_t padded = 1;
+    while (padded < bins)
+        padded <<= 1;
+    const size_t sorted_words = (words + 3) & ~(size_t) 3;
+    uint32_t *sorted = (uint32_t *) temp_alloc(sorted_words * 4 + (padded > RS_SMEM ? (size_t) padded * 8 : 0), stream);
+    if (!sorted)
+        return fail(B200_ERR_CUDA, "jit_var_call_reduce(): out of memory");
+    mkperm_sort_records_kernel<<<1, 1024, 0, stream>>>(records, bins, sorted,
+                                                       (unsigned long long *) (sorted + sorted_words));
+    count_launch();
+    int rc = cuda_fail(cudaMemcpyAsync(offsets, sorted, words * 4, cudaMemcpyDeviceToHost, stream),
+                       "cudaMemcpyAsync(offsets)");
+    temp_free(sorted, stream);
+    return rc;
+}
+
+
 /// starts[b] = number of keys below b = first slot of bucket b in the finished
 /// permutation, found by binary search over the permutation itself (keys are
 /// sorted along it).  For many buckets this beats a histogram of the keys, which
@@ -893,7 +960,7 @@ static int histogram_launch(cudaStream_t stream, const uint32_t *keys, uint64_t 
 /// Ranked-tile sort of every group of 'group_size' consecutive keys (group_size ==
 /// size: one group, the vcall case).  offsets: single group only.
 static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t size, uint32_t group_size,
-                         uint32_t bucket_count, uint32_t *perm, uint32_t *offsets) {
+                         uint32_t bucket_count, uint32_t *perm, uint32_t *offsets, bool by_size) {
     const uint32_t index_base = 0;
     uint32_t total_bits = 1;
     while (total_bits < 32 && (1ull << total_bits) < bucket_count)
@@ -999,12 +1066,11 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
             }
             mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(table, 2 * (uint64_t) ntiles, bucket_count, size, records);
             count_launch();
-            cudaError_t err = cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
-                                              cudaMemcpyDeviceToHost, stream);
+            rc = deliver_records(stream, records, bucket_count, offsets, by_size);
             temp_free(records, stream);
-            if (err != cudaSuccess) {
+            if (rc) {
                 cleanup();
-                return cuda_fail(err, "cudaMemcpyAsync(offsets)");
+                return rc;
             }
         }
         const uint32_t bits = form == RK_RAW1 ? std::max(3u, total_bits) : std::max(3u, width[p]);
@@ -1037,9 +1103,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
         if (!rc) {
             mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(hist, 1, bucket_count, size, records);
             count_launch();
-            rc = cuda_fail(cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
-                                           cudaMemcpyDeviceToHost, stream),
-                           "cudaMemcpyAsync(offsets)");
+            rc = deliver_records(stream, records, bucket_count, offsets, by_size);
         }
         temp_free(hist, stream);
         if (rc) {
@@ -1077,7 +1141,7 @@ int b200_mkperm_histogram(void *stream_, const uint32_t *values, uint64_t size,
 
 static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
                        uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
-                       uint32_t *offsets, uint32_t *unique, bool wait);
+                       uint32_t *offsets, uint32_t *unique, bool wait, bool by_size = false);
 
 int b200_block_mkperm(void *stream_, const uint32_t *values, uint32_t size,
                       uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
@@ -1091,9 +1155,27 @@ int b200_block_mkperm_async(void *stream_, const uint32_t *values, uint32_t size
     return mkperm_impl(stream_, values, size, block_size, bucket_count, perm, offsets, nullptr, false);
 }
 
+int b200_call_reduce(void *stream_, const uint32_t *ids, uint32_t size, uint32_t id_bound,
+                     uint32_t *perm, uint32_t *offsets, uint32_t *unique) {
+    if (id_bound == 0xffffffffu)
+        return fail(B200_ERR_INVALID, "jit_var_call_reduce(): too many callables!");
+    if (!offsets)
+        return fail(B200_ERR_INVALID, "jit_var_call_reduce(): the bucket records are required!");
+    return mkperm_impl(stream_, ids, size, size, id_bound + 1, perm, offsets, unique, true, true);
+}
+
+int b200_call_reduce_async(void *stream_, const uint32_t *ids, uint32_t size, uint32_t id_bound,
+                           uint32_t *perm, uint32_t *offsets) {
+    if (id_bound == 0xffffffffu)
+        return fail(B200_ERR_INVALID, "jit_var_call_reduce(): too many callables!");
+    if (!offsets)
+        return fail(B200_ERR_INVALID, "jit_var_call_reduce(): the bucket records are required!");
+    return mkperm_impl(stream_, ids, size, size, id_bound + 1, perm, offsets, nullptr, false, true);
+}
+
 static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
                        uint32_t block_size, uint32_t bucket_count, uint32_t *perm,
-                       uint32_t *offsets, uint32_t *unique, bool wait) {
+                       uint32_t *offsets, uint32_t *unique, bool wait, bool by_size) {
     int rc = ensure_init();
     if (rc)
         return rc;
@@ -1123,7 +1205,7 @@ static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
     // ranked tiles.  Smaller groups would leave the tiles mostly empty: row kernels.
     if (ngroups == 1 || block_size >= rk_tile_keys() / 2) {
         rc = mkperm_ranked(stream, values, size, block_size, bucket_count, perm,
-                           ngroups == 1 ? offsets : nullptr);
+                           ngroups == 1 ? offsets : nullptr, by_size);
         if (rc)
             return rc;
         if (wait && offsets && ngroups == 1) {
@@ -1239,12 +1321,11 @@ static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
                 mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(counts, rows_per_group, bucket_count,
                                                              size, records);
                 count_launch();
-                cudaError_t err = cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
-                                                  cudaMemcpyDeviceToHost, stream);
+                rc = deliver_records(stream, records, bucket_count, offsets, by_size);
                 temp_free(records, stream);
-                if (err != cudaSuccess) {
+                if (rc) {
                     cleanup();
-                    return cuda_fail(err, "cudaMemcpyAsync(offsets)");
+                    return rc;
                 }
             }
 
@@ -1276,9 +1357,7 @@ static int mkperm_impl(void *stream_, const uint32_t *values, uint32_t size,
         if (!rc) {
             mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(hist, 1, bucket_count, size, records);
             count_launch();
-            rc = cuda_fail(cudaMemcpyAsync(offsets, records, ((size_t) bucket_count * 4 + 1) * 4,
-                                           cudaMemcpyDeviceToHost, stream),
-                           "cudaMemcpyAsync(offsets)");
+            rc = deliver_records(stream, records, bucket_count, offsets, by_size);
         }
         temp_free(hist, stream);
         if (rc) {

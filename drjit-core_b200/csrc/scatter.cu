@@ -853,6 +853,120 @@ static ScatterFn pick_scatter(int vt, int op) {
     }
 }
 
+
+// ----------------------------------------------------------- 64-bit indices
+//
+// jitc_var_scatter accepts uint64 / int64 indices as well (src/op.cpp:2899-3086).
+// Same structure as the scalar kernel with the run merge of scatter_runs, on 64-bit
+// element offsets (valid signed indices are non-negative: same bits as unsigned).
+template <typename T, int Op, bool MERGE>
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_reduce_wide_kernel(T *__restrict__ target, const T *__restrict__ value,
+                           const uint64_t *__restrict__ index, const uint8_t *__restrict__ mask,
+                           uint64_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t) gridDim.x * SCATTER_THREADS;
+    const uint64_t first = (uint64_t) blockIdx.x * SCATTER_THREADS + threadIdx.x;
+    for (uint64_t base = first - lane; base < n; base += stride) {
+        const uint64_t i = base + lane;
+        bool on = i < n;
+        uint64_t idx = 0;
+        T v = T();
+        if (on) {
+            idx = __ldcs(index + i);
+            v = __ldcs(value + i);
+            if (mask)
+                on = __ldcs(mask + i) != 0;
+        }
+        bool issue = on;
+        if constexpr (MERGE) {
+            const uint64_t prev_idx = __shfl_up_sync(FULL_MASK, idx, 1);
+            const uint32_t active = __ballot_sync(FULL_MASK, on);
+            const bool head = lane == 0 || idx != prev_idx || !((active >> (lane - 1)) & 1u) || !on;
+            const uint32_t heads = __ballot_sync(FULL_MASK, head);
+            if (heads != FULL_MASK) {
+                const uint32_t above = heads & ~((2u << lane) - 1u);
+                const uint32_t last = above ? (uint32_t) __ffs(above) - 2u : 31u;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const T other = shfl_elem<T>(FULL_MASK, v, min(lane + d, 31u));
+                    if (lane + d <= last)
+                        v = ElemOp<T, Op>::apply(v, other);
+                }
+            }
+            issue = head && on;
+        }
+        if (issue)
+            Atomic<T, Op>::apply(target + idx, v);
+    }
+}
+
+struct WideCall {
+    cudaStream_t stream;
+    void *target;
+    const void *value;
+    const uint64_t *index;
+    const uint8_t *mask;
+    uint64_t n;
+    int mode;
+};
+
+template <typename T, int Op> static int launch_scatter_wide(const WideCall &c) {
+    uint32_t grid = (uint32_t) std::max<uint64_t>(
+        1, std::min<uint64_t>(ceil_div(c.n, (uint64_t) SCATTER_THREADS), (uint64_t) sm_count() * 16));
+    if (c.mode == B200_MODE_DIRECT || c.mode == B200_MODE_NO_CONFLICTS)
+        scatter_reduce_wide_kernel<T, Op, false><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+            (T *) c.target, (const T *) c.value, c.index, c.mask, c.n);
+    else
+        scatter_reduce_wide_kernel<T, Op, true><<<grid, SCATTER_THREADS, 0, c.stream>>>(
+            (T *) c.target, (const T *) c.value, c.index, c.mask, c.n);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+typedef int (*WideFn)(const WideCall &);
+
+template <typename T> static WideFn pick_wide(int op, bool is_int) {
+    switch (op) {
+        case B200_OP_ADD: return launch_scatter_wide<T, B200_OP_ADD>;
+        case B200_OP_MIN: return launch_scatter_wide<T, B200_OP_MIN>;
+        case B200_OP_MAX: return launch_scatter_wide<T, B200_OP_MAX>;
+    }
+    if constexpr (std::is_integral<T>::value) {
+        if (op == B200_OP_AND)
+            return launch_scatter_wide<T, B200_OP_AND>;
+        if (op == B200_OP_OR)
+            return launch_scatter_wide<T, B200_OP_OR>;
+    }
+    (void) is_int;
+    return nullptr;
+}
+
+/// packet.cu (b200_scatter_reduce_idx): (vt, op) has been validated by the caller
+int scatter_reduce_wide(cudaStream_t stream, int vt, int op, int mode, void *target, const void *value,
+                        const uint64_t *index, const uint8_t *mask, uint64_t n) {
+    WideFn fn = nullptr;
+    switch (vt) {
+        case B200_VT_INT32:   fn = pick_wide<int32_t>(op, true); break;
+        case B200_VT_UINT32:  fn = pick_wide<uint32_t>(op, true); break;
+        case B200_VT_INT64:   fn = pick_wide<long long>(op, true); break;
+        case B200_VT_UINT64:  fn = pick_wide<unsigned long long>(op, true); break;
+        case B200_VT_FLOAT16: fn = pick_wide<__half>(op, false); break;
+        case B200_VT_FLOAT32: fn = pick_wide<float>(op, false); break;
+        case B200_VT_FLOAT64: fn = pick_wide<double>(op, false); break;
+    }
+    if (!fn)
+        return fail(B200_ERR_UNSUPPORTED,
+                    "jit_var_scatter(): the %s backend does not support the requested type of "
+                    "atomic reduction (%s) for variables of type (%s)", "CUDA", op_name(op), type_name(vt));
+    WideCall call{ stream, target, value, index, mask, n, mode };
+    return fn(call);
+}
+
+/// packet.cu: float16 Add packets (red.global.v2 / .v4 / .v8.f16)
+int packet_f16_add(cudaStream_t stream, void *target, const void *const *values, uint32_t width,
+                   const uint32_t *index, const uint8_t *mask, uint64_t n, int mode);
+
 } // namespace b200
 
 using namespace b200;
@@ -861,8 +975,9 @@ extern "C" {
 
 int b200_can_scatter_reduce(int vt, int op) {
     // src/op.cpp:2735-2820 evaluated for the CUDA backend at compute capability 10.0
+    // (Identity -- the plain scatter -- is served by b200_scatter_reduce_idx)
     if (op == B200_OP_IDENTITY)
-        return 1;
+        return type_size(vt) != 0;
     return pick_scatter(vt, op) != nullptr;
 }
 
@@ -872,6 +987,8 @@ int b200_scatter_reduce(void *stream_, int vt, int op, int mode, void *target,
     int rc = ensure_init();
     if (rc)
         return rc;
+    if (op == B200_OP_IDENTITY) // plain scatter (packet.cu)
+        return b200_scatter_reduce_idx(stream_, vt, op, mode, target, value, index, B200_VT_UINT32, mask, n);
     ScatterFn fn = pick_scatter(vt, op);
     if (!fn)
         return fail(B200_ERR_UNSUPPORTED,
@@ -929,6 +1046,21 @@ int b200_scatter_reduce_packet(void *stream_, int vt, int op, int mode, void *ta
         return fail(B200_ERR_INVALID, "jit_var_scatter_packet(): vector size must be a power of two!");
     if (mode != B200_MODE_AUTO && mode != B200_MODE_DIRECT && mode != B200_MODE_LOCAL)
         return fail(B200_ERR_UNSUPPORTED, "jit_var_scatter_packet(): unsupported reduction mode %d", mode);
+    if (vt == B200_VT_FLOAT16 && op == B200_OP_ADD) {
+        if (width > 8)
+            return fail(B200_ERR_UNSUPPORTED,
+                        "jit_var_scatter_packet(): packet size must be 1, 2, 4 or 8 (got %u)", width);
+        // red.global.v2 / .v4 / .v8.f16 need naturally aligned packets
+        if ((uintptr_t) target % (width * 2) != 0)
+            return fail(B200_ERR_INVALID,
+                        "jit_var_scatter_packet(): the target of a float16 packet reduction must be "
+                        "aligned to %u bytes!", width * 2);
+        if (n == 0)
+            return B200_OK;
+        cudaStream_t stream = resolve_stream(stream_);
+        HistoryScope hs(stream, B200_KERNEL_SCATTER, n);
+        return packet_f16_add(stream, target, values, width, index, mask, n, mode);
+    }
     PacketFn fn = pick_packet(vt, op);
     if (!fn) {
         // no packet kernel for this (type, op): component by component

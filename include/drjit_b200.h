@@ -60,7 +60,8 @@ enum {
     B200_KERNEL_BLOCK_REDUCE = 1, B200_KERNEL_BLOCK_PREFIX_REDUCE = 2, B200_KERNEL_DOT = 3,
     B200_KERNEL_COMPRESS = 5, B200_KERNEL_MKPERM = 6, B200_KERNEL_MEMCPY = 7,
     B200_KERNEL_MEMSET = 8,
-    B200_KERNEL_SCATTER = 64 /* stand-alone scatter kernels: fused into JIT kernels in the reference */
+    B200_KERNEL_SCATTER = 64, /* stand-alone scatter kernels: fused into JIT kernels in the reference */
+    B200_KERNEL_GATHER = 65   /* stand-alone packet gather */
 };
 
 /* VarType values used on this path (jit.h:597-611) */
@@ -239,6 +240,21 @@ B200_API int b200_block_mkperm_async(void *stream, const uint32_t *values, uint3
                                      uint32_t block_size, uint32_t bucket_count,
                                      uint32_t *perm, uint32_t *offsets);
 
+/* The consumer of jit_block_mkperm in vectorised method dispatch, jitc_var_call_reduce
+ * (jit.h:2510, src/call.cpp:1268-1389), up to the point where it creates variables:
+ * callable ids in [0, id_bound] (0 = the null callable; the reference adds that bucket
+ * itself, call.cpp:1292) are grouped by jit_block_mkperm(size, size, id_bound + 1) and the
+ * (id, start, size, 0) records of the non-empty buckets arrive in `offsets` (host
+ * accessible, 4 * (id_bound + 1) + 1 words) ALREADY ORDERED BY SIZE, largest first
+ * (ties: ascending id) -- the order the reference establishes with a host-side std::sort
+ * after its event wait (call.cpp:1346-1352; std::sort leaves the order of ties open).
+ * offsets[4 * (id_bound + 1)] and *unique = number of records.  perm[start .. start + size)
+ * of a record are the (stable) element indices of that callable. */
+B200_API int b200_call_reduce(void *stream, const uint32_t *ids, uint32_t size, uint32_t id_bound,
+                              uint32_t *perm, uint32_t *offsets, uint32_t *unique);
+B200_API int b200_call_reduce_async(void *stream, const uint32_t *ids, uint32_t size,
+                                    uint32_t id_bound, uint32_t *perm, uint32_t *offsets);
+
 /* Phase 1 of the above on its own (per-bucket counts of the whole array into
  * device memory hist[bucket_count]); the multi-GPU front end all-reduces it. */
 B200_API int b200_mkperm_histogram(void *stream, const uint32_t *values, uint64_t size,
@@ -274,11 +290,39 @@ B200_API int b200_scatter_inc(void *stream, uint32_t *target, const uint32_t *in
  * src/cuda_packet.cpp:169-327):
  *   if (mask == NULL || mask[i]) target[index[i] * width + k] op= values[k][i], k < width
  * width in {1, 2, 4, 8}; values: HOST array of `width` device pointers (the
- * reference takes `width` separate variables).  f32 / f64 Add, f32 Min / Max,
- * u32 / i32 integer operations.  f32 Add issues red.global.add.v2/.v4.f32. */
+ * reference takes `width` separate variables).  f16 / f32 / f64 Add, f32 Min / Max,
+ * u32 / i32 integer operations.  f32 Add issues red.global.add.v2/.v4.f32, f16 Add
+ * red.global.v2/.v4/.v8.f16.add.noftz (src/cuda_packet.cpp:229-266); those need the
+ * target aligned to min(width * sizeof(T), 16) bytes. */
 B200_API int b200_scatter_reduce_packet(void *stream, int vt, int op, int mode, void *target,
                                         const void *const *values, uint32_t width,
                                         const uint32_t *index, const uint8_t *mask, uint64_t n);
+
+/* b200_scatter_reduce with the other index types the reference accepts (int32, uint64,
+ * int64; jitc_var_scatter, src/op.cpp:2899-3086) and with op == Identity: the plain
+ * scatter target[index[i]] = value[i] of any 1 / 2 / 4 / 8 byte type (duplicate
+ * indices: one of the values wins).  index_vt: VarType of the index array. */
+B200_API int b200_scatter_reduce_idx(void *stream, int vt, int op, int mode, void *target,
+                                     const void *value, const void *index, int index_vt,
+                                     const uint8_t *mask, uint64_t n);
+
+/* jit_var_scatter_packet WITHOUT reduction (jit.h:1117 with ReduceOp::Identity; emitter
+ * jitc_cuda_render_scatter_packet, src/cuda_packet.cpp:329-443):
+ *   if (mask == NULL || mask[i]) target[index[i] * width + k] = values[k][i], k < width
+ * for any 1 / 2 / 4 / 8 byte type, width in {1, 2, 4, 8}; a packet leaves in vector
+ * stores of up to 128 bits. */
+B200_API int b200_scatter_packet(void *stream, int vt, void *target, const void *const *values,
+                                 uint32_t width, const uint32_t *index, const uint8_t *mask,
+                                 uint64_t n);
+
+/* Stand-alone form of jit_var_gather_packet (jit.h:981; emitter
+ * jitc_cuda_render_gather_packet, src/cuda_packet.cpp:18-166): array-of-structures ->
+ * structure-of-arrays,
+ *   out[k][i] = (mask == NULL || mask[i]) ? source[index[i] * width + k] : 0,  k < width
+ * with vector loads of up to 128 bits.  out: HOST array of `width` device pointers. */
+B200_API int b200_gather_packet(void *stream, int vt, const void *source, void *const *out,
+                                uint32_t width, const uint32_t *index, const uint8_t *mask,
+                                uint64_t n);
 
 /* --------------------------------------------------------------- multi-GPU */
 

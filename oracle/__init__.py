@@ -118,6 +118,31 @@ class Oracle:
         return tgt.reshape(-1)
 
     @staticmethod
+    def scatter_packet(target, values, index, mask=None):
+        """src/cuda_packet.cpp:329-443 applied serially (element order): target[index * W
+        + k] = values[k].  With duplicate indices the reference leaves it open which value
+        wins; callers compare only inputs without active duplicates."""
+        width = len(values)
+        tgt = target.copy().reshape(-1, width)
+        on = np.ones(index.shape[0], dtype=bool) if mask is None else mask.astype(bool)
+        for k in range(width):
+            tgt[index[on], k] = values[k][on]
+        return tgt.reshape(-1)
+
+    @staticmethod
+    def gather_packet(source, width, index, mask=None):
+        """src/cuda_packet.cpp:18-166: out[k][i] = source[index[i] * W + k], masked-off
+        lanes read 0 (:52-56)."""
+        src = source.reshape(-1, width)
+        on = np.ones(index.shape[0], dtype=bool) if mask is None else mask.astype(bool)
+        outs = []
+        for k in range(width):
+            o = np.zeros(index.shape[0], dtype=source.dtype)
+            o[on] = src[index[on], k]
+            outs.append(o)
+        return outs
+
+    @staticmethod
     def scatter_inc_check(target_before, target_after, index, mask, out):
         """Semantics of src/cuda_scatter.cpp:356-393 (the order in which entries of
         one counter are served is unspecified): every counter grows by the number

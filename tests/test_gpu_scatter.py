@@ -225,3 +225,119 @@ def test_scatter_reduce_packet(dr, O, width):
     assert not bad, bad[:10]
     with pytest.raises(RuntimeError):  # vector size must be a power of two
         dr.scatter_reduce_packet(VT["f32"], OP["add"], 0, [0, 0, 0], 0, None, 1)
+
+
+@pytest.mark.parametrize("width", [1, 2, 4, 8])
+def test_scatter_packet_f16_add(dr, O, width):
+    # red.global.v2 / .v4 / .v8.f16.add.noftz (src/cuda_packet.cpp:229-266): every addition
+    # rounds to f16 -> count * ulp / 2 of accumulated error allowed, as in test_scatter_f16
+    bad = []
+    n, m = 20011, 509
+    for kind in ("random", "runs", "same"):
+        idx = index_input(n, m, kind)
+        mask = (fmix32(u32_input(n)) & np.uint32(3) != 0).astype(np.uint8)
+        vals = [((f32_input(n) * 0.01) + 0.001 * k).astype(np.float16) for k in range(width)]
+        for mname, mode in MODES.items():
+            for mk in (None, mask):
+                d_t = to_dev(np.zeros(m * width, dtype=np.float16))
+                dr.scatter_reduce_packet(VT["f16"], OP["add"], d_t, [to_dev(v) for v in vals], to_dev(idx),
+                                         None if mk is None else to_dev(mk), n, mode=mode)
+                got = to_host(d_t, np.float16).astype(np.float64)
+                ref = O.scatter_reduce_packet(VT["f16"], OP["add"], np.zeros(m * width, dtype=np.float16),
+                                              vals, idx, mk, wide=True).astype(np.float64)
+                on = np.ones(n, bool) if mk is None else mk.astype(bool)
+                cnt = np.repeat(np.bincount(idx[on], minlength=m), width)
+                tol = np.maximum(cnt, 1) * (2.0 ** -11) * np.maximum(ref, 1e-3)
+                if np.any(np.abs(got - ref) > tol):
+                    bad.append((kind, mname, mk is not None))
+    assert not bad, bad[:10]
+    if width > 1:
+        with pytest.raises(RuntimeError):  # misaligned target of a vector reduction
+            t = to_dev(np.zeros(m * width + 1, dtype=np.float16))
+            dr.scatter_reduce_packet(VT["f16"], OP["add"], t.data_ptr() + 2, [0] * width, 0, None, 1)
+
+
+@pytest.mark.parametrize("tname,dt", [("u8", np.uint8), ("f16", np.float16), ("u32", np.uint32), ("f32", np.float32),
+                                      ("f64", np.float64), ("u64", np.uint64)])
+def test_packet_scatter_and_gather(dr, O, tname, dt):
+    # non-reducing packet scatter (src/cuda_packet.cpp:329-443) with a permutation as index
+    # (no duplicate targets: the result is defined), packet gather (:18-166) with arbitrary
+    # indices; both bit-exact, every width, masked and unmasked, odd base alignment
+    bad = []
+    n = 50021
+    vt = VT[tname]
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(n).astype(np.uint32)
+    gidx = (fmix32(u32_input(n)) % np.uint32(n)).astype(np.uint32)
+    mask = (fmix32(u32_input(n) ^ np.uint32(0xABCD)) & np.uint32(3) != 0).astype(np.uint8)
+    for width in (1, 2, 4, 8):
+        vals = [(u32_input(n) >> np.uint32(k)).astype(dt) if np.issubdtype(dt, np.integer)
+                else ((u32_input(n) >> np.uint32(8 + k)).astype(np.float32) * np.float32(2.0 ** -20)).astype(dt)
+                for k in range(width)]
+        for off in (0, 1):  # element offset of the AoS base: exercises the narrower chunk sizes
+            for mk in (None, mask):
+                base = np.full(n * width + off, 7, dtype=dt)
+                d_b = to_dev(base)
+                view = d_b.data_ptr() + off * base.itemsize
+                dr.scatter_packet(vt, view, [to_dev(v) for v in vals], to_dev(perm),
+                                  None if mk is None else to_dev(mk), n)
+                ref = O.scatter_packet(base[off:], vals, perm, mk)
+                got = to_host(d_b, dt)
+                if not np.array_equal(got[off:].view(np.uint8), ref.view(np.uint8)) or (off and got[0] != 7):
+                    bad.append(("scatter", width, off, mk is not None))
+                src = np.concatenate([np.zeros(off, dtype=dt), np.stack(vals, axis=1).reshape(-1)])
+                d_s = to_dev(src)
+                outs = [empty_dev(n, dt) for _ in range(width)]
+                dr.gather_packet(vt, d_s.data_ptr() + off * src.itemsize, outs, to_dev(gidx),
+                                 None if mk is None else to_dev(mk), n)
+                refs = O.gather_packet(src[off:], width, gidx, mk)
+                for k in range(width):
+                    if not np.array_equal(to_host(outs[k], dt).view(np.uint8), refs[k].view(np.uint8)):
+                        bad.append(("gather", width, off, mk is not None, k))
+    assert not bad, bad[:10]
+    with pytest.raises(RuntimeError):  # vector size must be a power of two
+        dr.scatter_packet(vt, 0, [0, 0, 0], 0, None, 1)
+
+
+@pytest.mark.parametrize("iname,idt", [("i32", np.int32), ("u64", np.uint64), ("i64", np.int64)])
+def test_scatter_index_types_and_identity(dr, O, iname, idt):
+    # jitc_var_scatter accepts int32 / uint64 / int64 indices (src/op.cpp:2899-3086);
+    # ReduceOp::Identity is the plain scatter
+    bad = []
+    n, m = 70001, 4099
+    for kind in ("random", "runs", "same"):
+        idx = index_input(n, m, kind)
+        mask = (fmix32(u32_input(n)) & np.uint32(3) != 0).astype(np.uint8)
+        ival = (u32_input(n) >> np.uint32(9)).astype(np.uint32)
+        fval = f32_input(n)
+        for mname, mode in MODES.items():
+            for mk in (None, mask):
+                d_m = None if mk is None else to_dev(mk)
+                for opn in ("add", "min", "max", "and_", "or_"):
+                    ident = O.reduce_identity(VT["u32"], OP[opn]) & 0xFFFFFFFF
+                    tgt = np.full(m, ident, dtype=np.uint32)
+                    d_t = to_dev(tgt)
+                    dr.scatter_reduce_idx(VT["u32"], OP[opn], d_t, to_dev(ival), to_dev(idx.astype(idt)), VT[iname],
+                                          d_m, n, mode=mode)
+                    if not np.array_equal(to_host(d_t, np.uint32), O.scatter_reduce(VT["u32"], OP[opn], tgt, ival, idx, mk)):
+                        bad.append((kind, mname, mk is not None, opn))
+                d_t = to_dev(np.zeros(m, dtype=np.float32))
+                dr.scatter_reduce_idx(VT["f32"], OP["add"], d_t, to_dev(fval), to_dev(idx.astype(idt)), VT[iname],
+                                      d_m, n, mode=mode)
+                ref = O.scatter_reduce(VT["f32"], OP["add"], np.zeros(m, dtype=np.float32), fval, idx, mk, wide=True)
+                if not np.allclose(to_host(d_t, np.float32), ref, rtol=2e-5, atol=1e-30):  # fp32 Add: 2e-5 relative
+                    bad.append((kind, mname, mk is not None, "f32 add"))
+    # plain scatter through a permutation (no duplicates): defined result, bit-exact
+    perm = np.random.default_rng(3).permutation(n).astype(idt)
+    for tname, dt in (("u8", np.uint8), ("f16", np.float16), ("f32", np.float32), ("f64", np.float64)):
+        val = (u32_input(n) >> np.uint32(5)).astype(dt)
+        for mk in (None, mask):
+            tgt = np.full(n, 3, dtype=dt)
+            d_t = to_dev(tgt)
+            dr.scatter_reduce_idx(VT[tname], OP["identity"] if "identity" in OP else 0, d_t, to_dev(val), to_dev(perm),
+                                  VT[iname], None if mk is None else to_dev(mk), n)
+            ref = O.scatter_packet(tgt, [val], perm.astype(np.int64), mk)
+            if not np.array_equal(to_host(d_t, dt).view(np.uint8), ref.view(np.uint8)):
+                bad.append(("identity", tname, mk is not None))
+    assert not bad, bad[:10]
+    assert dr.jit_can_scatter_reduce(1, VT["f32"], 0)  # Identity: the plain scatter exists
