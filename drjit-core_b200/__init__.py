@@ -111,6 +111,8 @@ def lib():
         L.b200_scatter_reduce.argtypes = [vp, i, i, i, vp, vp, vp, vp, u64]
         L.b200_scatter_inc.argtypes = [vp, vp, vp, vp, vp, u64]
         L.b200_scatter_reduce_packet.argtypes = [vp, i, i, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
+        L.b200_call_reduce.argtypes = [vp, vp, u32, u32, vp, vp, ctypes.POINTER(u32)]
+        L.b200_call_reduce_async.argtypes = [vp, vp, u32, u32, vp, vp]
         L.b200_scatter_reduce_idx.argtypes = [vp, i, i, i, vp, vp, vp, i, vp, u64]
         L.b200_scatter_packet.argtypes = [vp, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
         L.b200_gather_packet.argtypes = [vp, i, vp, ctypes.POINTER(vp), u32, vp, vp, u64]
@@ -363,6 +365,17 @@ def block_mkperm_async(values, size, block_size, bucket_count, perm, offsets, st
     """Enqueue only; after a stream sync offsets[4 * bucket_count] is the unique count."""
     _check(lib().b200_block_mkperm_async(_stream(stream), _ptr(values), size, block_size,
                                          bucket_count, _ptr(perm), _ptr(offsets)))
+
+
+def call_reduce(ids, size, id_bound, perm, offsets, stream=None):
+    """The mkperm step of jit_var_call_reduce (src/call.cpp:1268-1389): callable ids in
+    [0, id_bound] -> permutation + (id, start, size, 0) records ordered by size (largest
+    first, ties by ascending id) in the host-accessible `offsets` (4 * (id_bound + 1) + 1
+    words).  Returns the number of records."""
+    u = ctypes.c_uint32(0)
+    _check(lib().b200_call_reduce(_stream(stream), _ptr(ids), size, id_bound, _ptr(perm),
+                                  _ptr(offsets), ctypes.byref(u)))
+    return u.value
 
 
 def mkperm_histogram(values, size, bucket_count, hist, stream=None):

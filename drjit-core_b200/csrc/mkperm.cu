@@ -356,22 +356,113 @@ static int deliver_records(cudaStream_t stream, const uint32_t *records, uint32_
 /// sorted along it).  For many buckets this beats a histogram of the keys, which
 /// no longer fits one shared-memory table: 26 dependent steps of two gathers per
 /// bucket against another one or two sweeps over all keys.
+/// Sixteen lanes per bucket probe sixteen pivots of the remaining range at once
+/// (17-ary search: 7 dependent steps for 2^26 keys instead of 26).
 __global__ void __launch_bounds__(256)
 mkperm_bounds_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ perm,
                      uint32_t size, uint32_t index_base, uint32_t bins, uint32_t *__restrict__ starts) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= bins)
-        return;
-    uint32_t lo = 0, hi = size; // first position whose key is >= b
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        const uint32_t k = min(__ldg(keys + (__ldg(perm + mid) - index_base)), bins - 1);
-        if (k < b)
-            lo = mid + 1;
-        else
-            hi = mid;
+    const uint32_t sub = threadIdx.x & 15, lane = threadIdx.x & 31;
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const uint32_t group = 0xffffu << (lane & 16); // the lanes of this bucket
+    const bool valid = b < bins; // (uniform per group of 16 lanes; all lanes take part in the shuffles)
+    uint32_t lo = 0, hi = valid ? size : 0; // first position whose key is >= b lies in [lo, hi]
+    auto key_at = [&](uint32_t pos) {
+        return min(__ldg(keys + (__ldg(perm + pos) - index_base)), bins - 1);
+    };
+    while (__any_sync(FULL_MASK, hi - lo > 16)) {
+        const uint32_t len = hi - lo;
+        if (len > 16) {
+            // pivots lo + ceil((j + 1) * len / 17) - 1 < hi, ascending in j = 0 .. 15
+            const uint32_t piv = lo + (uint32_t) (((uint64_t) (sub + 1) * len + 16) / 17) - 1;
+            const uint32_t ge = __ballot_sync(group, key_at(piv) >= b) & group;
+            // first pivot whose key is >= b bounds the answer from above, the one before from below
+            const uint32_t j = ge ? (uint32_t) __ffs(ge) - 1 - (lane & 16) : 16;
+            const uint32_t piv_hi = __shfl_sync(group, piv, (lane & 16) + min(j, 15u));
+            const uint32_t piv_lo = __shfl_sync(group, piv, (lane & 16) + (j ? j - 1 : 0));
+            if (j < 16)
+                hi = piv_hi;
+            if (j > 0)
+                lo = piv_lo + 1;
+        }
     }
-    starts[b] = lo;
+    // at most 16 candidates left: [lo, hi)
+    const uint32_t pos = lo + sub;
+    const bool ge = pos >= hi || key_at(pos) >= b;
+    const uint32_t m = __ballot_sync(group, ge) & group;
+    if (valid && sub == 0)
+        starts[b] = m ? lo + (uint32_t) __ffs(m) - 1 - (lane & 16) : hi;
+}
+
+/// mkperm_offsets_kernel for many buckets, in two launches of one CTA per 1024 buckets:
+/// `count` = non-empty buckets per CTA, `emit` sums the counts in front of it and writes
+/// the records (ascending id).  starts[b] = first output slot of bucket b.
+__global__ void __launch_bounds__(1024)
+mkperm_offsets_count_kernel(const uint32_t *__restrict__ starts, uint32_t bins, uint32_t size,
+                            uint32_t *__restrict__ block_counts) {
+    const uint32_t b = blockIdx.x * 1024 + threadIdx.x;
+    bool nonempty = false;
+    if (b < bins)
+        nonempty = (b + 1 < bins ? __ldg(starts + b + 1) : size) != __ldg(starts + b);
+    const uint32_t c = (uint32_t) __syncthreads_count(nonempty);
+    if (threadIdx.x == 0)
+        block_counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+mkperm_offsets_emit_kernel(const uint32_t *__restrict__ starts, uint32_t bins, uint32_t size,
+                           const uint32_t *__restrict__ block_counts, uint32_t *__restrict__ records) {
+    __shared__ uint32_t s_part[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // records in front of this CTA (and, for the last CTA, in total)
+    uint32_t before = 0;
+    for (uint32_t i = tid; i < blockIdx.x; i += 1024)
+        before += __ldg(block_counts + i);
+    before = __reduce_add_sync(FULL_MASK, before);
+    if (lane == 0)
+        s_part[warp] = before;
+    __syncthreads();
+    before = 0;
+    #pragma unroll
+    for (int w = 0; w < 32; ++w)
+        before += s_part[w];
+    __syncthreads();
+    const uint32_t b = blockIdx.x * 1024 + tid;
+    uint32_t st = 0, nx = 0;
+    if (b < bins) {
+        st = __ldg(starts + b);
+        nx = b + 1 < bins ? __ldg(starts + b + 1) : size;
+    }
+    const bool nonempty = b < bins && nx != st;
+    const uint32_t flags = __ballot_sync(FULL_MASK, nonempty);
+    if (lane == 0)
+        s_part[warp] = __popc(flags);
+    __syncthreads();
+    uint32_t rec = before, total = 0;
+    #pragma unroll
+    for (uint32_t w = 0; w < 32; ++w) {
+        const uint32_t c = s_part[w];
+        rec += w < warp ? c : 0u;
+        total += c;
+    }
+    if (nonempty)
+        ((uint4 *) records)[rec + __popc(flags & ((1u << lane) - 1u))] = make_uint4(b, st, nx - st, 0);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0)
+        records[4 * (size_t) bins] = before + total;
+}
+
+/// Records from contiguous bucket starts (starts[b], b < bins): one CTA up to 8192
+/// buckets, the two-launch form beyond.  `scratch`: ceil(bins / 1024) words.
+static void offsets_from_starts(cudaStream_t stream, const uint32_t *starts, uint32_t bins, uint32_t size,
+                                uint32_t *records, uint32_t *scratch) {
+    if (bins <= 8192) {
+        mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(starts, 1, bins, size, records);
+        count_launch();
+        return;
+    }
+    const uint32_t grid = (uint32_t) ceil_div(bins, 1024);
+    mkperm_offsets_count_kernel<<<grid, 1024, 0, stream>>>(starts, bins, size, scratch);
+    mkperm_offsets_emit_kernel<<<grid, 1024, 0, stream>>>(starts, bins, size, scratch, records);
+    count_launch(2);
 }
 
 // ------------------------------------------------ single sorting group: tiles
@@ -1087,22 +1178,22 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
     // several passes: the bucket starts are read off the finished permutation
     if (npasses > 1 && offsets && ngroups == 1) {
         size_t hist_words = ((size_t) bucket_count + 3) & ~(size_t) 3; // keep records 16-byte aligned
-        uint32_t *hist = (uint32_t *) temp_alloc((hist_words + (size_t) bucket_count * 4 + 1) * 4, stream);
+        const size_t rec_words = ((size_t) bucket_count * 4 + 1 + 3) & ~(size_t) 3;
+        uint32_t *hist = (uint32_t *) temp_alloc((hist_words + rec_words + ceil_div(bucket_count, 1024)) * 4, stream);
         if (!hist) {
             cleanup();
             return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
         }
-        uint32_t *records = hist + hist_words;
-        // bucket starts: binary search over the finished permutation (35 us, latency
-        // bound, independent of the bucket count) instead of a histogram of the keys
-        // (49 us + a scan for <= 49152 buckets, a sweep per 49152 buckets beyond)
+        uint32_t *records = hist + hist_words, *block_counts = records + rec_words;
+        // bucket starts: 17-ary search over the finished permutation (latency bound,
+        // independent of the bucket count) instead of a histogram of the keys (49 us + a
+        // scan for <= 49152 buckets, a sweep per 49152 buckets beyond)
         int rc = B200_OK;
-        mkperm_bounds_kernel<<<(uint32_t) ceil_div(bucket_count, 256), 256, 0, stream>>>(
+        mkperm_bounds_kernel<<<(uint32_t) ceil_div((uint64_t) bucket_count * 16, 256), 256, 0, stream>>>(
             values, perm, size, index_base, bucket_count, hist);
         count_launch();
         if (!rc) {
-            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(hist, 1, bucket_count, size, records);
-            count_launch();
+            offsets_from_starts(stream, hist, bucket_count, size, records, block_counts);
             rc = deliver_records(stream, records, bucket_count, offsets, by_size);
         }
         temp_free(hist, stream);

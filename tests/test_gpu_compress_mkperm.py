@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from cases import cubic_sizes, key_input, mask_input
+from cases import cubic_sizes, fmix32, key_input, mask_input
 from util import empty_dev, to_dev, to_host
 
 pytestmark = pytest.mark.gpu
@@ -233,4 +233,31 @@ def test_compress_nonbinary_mask_bytes(dr):
         idx, cnt = run_compress(dr, m)
         if cnt != expect.size or not np.array_equal(idx, expect):
             bad.append((size, cnt, expect.size))
+    assert not bad, bad
+
+
+def test_call_reduce_records_by_size(dr, O):
+    # the mkperm step of jitc_var_call_reduce (src/call.cpp:1268-1389): ids in [0, id_bound]
+    # (0 = null callable), bucket_count = id_bound + 1 (call.cpp:1292), records sorted by
+    # size, largest first (call.cpp:1346-1352) -- ties by ascending id here.  The
+    # permutation equals jit_block_mkperm's; the records are the oracle's, re-sorted.
+    import torch
+    bad = []
+    for size in (1, 31, 1000, 40000, 300007):
+        for id_bound in (1, 3, 15, 100, 1023, 5000, 70000):
+            ids = key_input(size, id_bound + 1)
+            if size > 100:  # skew: a dominant callable and a rare null bucket
+                ids = np.where(fmix32(np.arange(size, dtype=np.uint32) ^ np.uint32(77)) % np.uint32(10) < 6,
+                               np.uint32(min(2, id_bound)), ids).astype(np.uint32)
+            buckets = id_bound + 1
+            d_perm = empty_dev(size, np.uint32)
+            offsets = torch.zeros(4 * buckets + 1, dtype=torch.int32).pin_memory()
+            uq = dr.call_reduce(to_dev(ids), size, id_bound, d_perm, offsets)
+            rperm, roffs, ruq = O.block_mkperm(ids, size, buckets)
+            rec = roffs[:4 * ruq].reshape(-1, 4)
+            order = np.lexsort((rec[:, 0], -rec[:, 2].astype(np.int64)))
+            got = offsets.numpy().view(np.uint32)
+            if uq != ruq or got[4 * buckets] != uq or not np.array_equal(to_host(d_perm, np.uint32), rperm) or \
+               not np.array_equal(got[:4 * uq].reshape(-1, 4), rec[order]):
+                bad.append((size, id_bound, uq, ruq))
     assert not bad, bad

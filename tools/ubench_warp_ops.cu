@@ -11,11 +11,12 @@
 #define THREADS 1024
 
 enum { MATCH32, MATCH16, MATCH4, MATCH1, BALLOT, SHFL, ATOMS_ADD32, ATOMS_ADD16, ATOMS_ADD4, ATOMS_ADD1,
-       ATOMS_OR32, ATOMS_OR4, REDUX, LDS_STS, POPC, NTESTS };
+       ATOMS_OR32, ATOMS_OR4, REDUX, LDS_STS, POPC, ATOMS_NORET32, ATOMS_NORET_STRIDED, LDS_ONLY, STS_ONLY, LDS128_ONLY, NTESTS };
 static const char *names[NTESTS] = { "match.any 32 distinct", "match.any 16 distinct", "match.any 4 distinct",
     "match.any 1 distinct", "vote.ballot", "shfl.idx", "atoms.add(ret) 32 addr", "atoms.add(ret) 16 addr",
     "atoms.add(ret) 4 addr", "atoms.add(ret) 1 addr", "atoms.or(noret) 32 addr", "atoms.or(noret) 4 addr",
-    "redux.add", "lds+sts private", "popc" };
+    "redux.add", "lds+sts private", "popc", "atoms.add(noret) 32 addr", "atoms.add(noret) own column", "lds independent",
+    "sts independent", "lds.128 independent" };
 
 template <int TEST> __global__ void __launch_bounds__(THREADS) bench(uint32_t *out, long long *cycles) {
     __shared__ uint32_t s[32][64];
@@ -43,6 +44,11 @@ template <int TEST> __global__ void __launch_bounds__(THREADS) bench(uint32_t *o
         if (TEST == REDUX) acc += __reduce_add_sync(0xffffffffu, x);
         if (TEST == LDS_STS) { uint32_t o = s[warp][(lane + i) & 63]; s[warp][(lane + i) & 63] = o + x; acc += o; }
         if (TEST == POPC) acc += __popc(x);
+        if (TEST == ATOMS_NORET32) atomicAdd(&s[warp][lane + (i & 32)], 1u);
+        if (TEST == ATOMS_NORET_STRIDED) atomicAdd(&((uint32_t *) s)[((x >> 7) & 15) * 128 + (threadIdx.x & 127)], 1u << (16 * (warp >> 4)));
+        if (TEST == LDS_ONLY) acc += s[warp][(lane + i) & 63];
+        if (TEST == STS_ONLY) s[warp][(lane + i) & 63] = x;
+        if (TEST == LDS128_ONLY) { uint4 q = ((const uint4 *) s)[(warp * 16 + ((lane + i) & 15))]; acc += q.x + q.w; }
     }
     long long t1 = clock64();
     if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -76,5 +82,7 @@ int main() {
     run<ATOMS_ADD32>(out, cyc, sms); run<ATOMS_ADD16>(out, cyc, sms); run<ATOMS_ADD4>(out, cyc, sms);
     run<ATOMS_ADD1>(out, cyc, sms); run<ATOMS_OR32>(out, cyc, sms); run<ATOMS_OR4>(out, cyc, sms);
     run<REDUX>(out, cyc, sms); run<LDS_STS>(out, cyc, sms); run<POPC>(out, cyc, sms);
+    run<ATOMS_NORET32>(out, cyc, sms); run<ATOMS_NORET_STRIDED>(out, cyc, sms); run<LDS_ONLY>(out, cyc, sms);
+    run<STS_ONLY>(out, cyc, sms); run<LDS128_ONLY>(out, cyc, sms);
     return 0;
 }
