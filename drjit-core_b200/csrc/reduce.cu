@@ -315,7 +315,8 @@ template <typename T, int Op, int TEAM, bool PARTIAL, int U>
 __global__ void __launch_bounds__(REDUCE_THREADS)
 reduce_chunks_kernel(const T *__restrict__ in, void *__restrict__ out_, uint64_t size,
                      uint64_t bs, uint64_t chunk, uint32_t chunks_per_block,
-                     uint64_t nteams) {
+                     uint64_t nteams, unsigned int *ticket = nullptr, T *final_out = nullptr,
+                     uint64_t nblocks = 0) {
     using V = typename ValueOf<T>::type;
     using R = Red<V, Op>;
     constexpr int N = VecInfo<T>::N;
@@ -400,6 +401,35 @@ reduce_chunks_kernel(const T *__restrict__ in, void *__restrict__ out_, uint64_t
                 ((V *) out_)[p] = r;
             else
                 ((T *) out_)[p] = from_value<T>(r);
+        }
+    }
+
+    // PARTIAL with a ticket: the CTA that finishes last combines the partials of every
+    // block in a fixed order (a warp per block, as reduce_finish_kernel) -- one launch,
+    // run-to-run deterministic floating point sums -- and leaves the ticket at zero
+    if constexpr (PARTIAL) {
+        if (ticket) {
+            __shared__ bool last;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0)
+                last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+            __syncthreads();
+            if (!last)
+                return;
+            __threadfence();
+            const V *partials = (const V *) out_;
+            const uint32_t lane = threadIdx.x & 31;
+            for (uint64_t b = threadIdx.x >> 5; b < nblocks; b += REDUCE_THREADS / 32) {
+                V acc = R::identity();
+                for (uint32_t i = lane; i < chunks_per_block; i += 32)
+                    acc = R::apply(acc, __ldcg(partials + b * chunks_per_block + i));
+                acc = warp_reduce<V, Op>(acc);
+                if (lane == 0)
+                    final_out[b] = from_value<T>(acc);
+            }
+            if (threadIdx.x == 0)
+                *ticket = 0;
         }
     }
 }
@@ -575,6 +605,15 @@ template <typename T, int Op> static int launch_block_reduce(const ReduceCall &c
     if (!partials)
         return fail(B200_ERR_CUDA, "jit_block_reduce(): out of memory (%zu bytes)",
                     (size_t) (nteams * sizeof(V)));
+    // few blocks: one launch, the last CTA finishes (no second kernel in the stream)
+    unsigned int *ticket = nblocks <= 64 ? stream_ticket(c.stream) : nullptr;
+    if (ticket) {
+        reduce_chunks_kernel<T, Op, REDUCE_THREADS, true, U><<<grid, REDUCE_THREADS, 0, c.stream>>>(
+            in, partials, size, bs, chunk, (uint32_t) chunks, nteams, ticket, out, nblocks);
+        temp_free(partials, c.stream);
+        B200_LAUNCH_CHECK();
+        return B200_OK;
+    }
     reduce_chunks_kernel<T, Op, REDUCE_THREADS, true, U><<<grid, REDUCE_THREADS, 0, c.stream>>>(
         in, partials, size, bs, chunk, (uint32_t) chunks, nteams);
     count_launch();

@@ -231,6 +231,38 @@ void temp_free(void *ptr, cudaStream_t stream) {
         cudaFreeAsync(ptr, stream);
 }
 
+// One ticket word per (device, stream), handed out from a per-device block of device
+// memory that is zeroed once.
+unsigned int *stream_ticket(cudaStream_t stream) {
+    constexpr int SLOTS = 1024;
+    struct Table {
+        unsigned int *words = nullptr;
+        std::vector<cudaStream_t> owners;
+    };
+    static std::mutex mutex;
+    static std::vector<Table> tables;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> guard(mutex);
+    if ((int) tables.size() <= dev)
+        tables.resize(dev + 1);
+    Table &t = tables[dev];
+    if (!t.words) {
+        if (cudaMalloc((void **) &t.words, SLOTS * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(t.words, 0, SLOTS * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError();
+            t.words = nullptr;
+            return nullptr;
+        }
+    }
+    for (size_t i = 0; i < t.owners.size(); ++i)
+        if (t.owners[i] == stream)
+            return t.words + i;
+    if ((int) t.owners.size() == SLOTS)
+        return nullptr;
+    t.owners.push_back(stream);
+    return t.words + (t.owners.size() - 1);
+}
+
 // One pinned host word per calling thread.  Kernels of the synchronising entry
 // points (jit_compress) write their scalar result straight into it (pinned memory
 // is device-accessible under unified addressing), so the host reads it after the
