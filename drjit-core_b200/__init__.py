@@ -15,7 +15,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libdrjit_core_b200.so")
+# (B200_LIB_PATH: development builds, e.g. the scan tuning build of tools/tune_scan.py)
+_LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libdrjit_core_b200.so")
 
 
 # ---- reference enums (jit.h:47-61, :597-611, :990-1014, :1017-1066) ----------
@@ -122,6 +123,7 @@ def lib():
         L.b200_sharded_destroy.argtypes = [vp]
         L.b200_sharded_reduce.argtypes = [vp, vp, i, i, vp, u64, vp]
         L.b200_sharded_prefix_reduce.argtypes = [vp, vp, i, i, u64, i, i, vp, vp]
+        L.b200_sharded_prefix_reduce_cyclic.argtypes = [vp, vp, i, i, u64, u64, i, vp, vp]
         L.b200_sharded_histogram.argtypes = [vp, vp, vp, u64, u32, vp, vp]
         L.b200_all_async.argtypes = [vp, vp, u64, vp]
         L.b200_any_async.argtypes = [vp, vp, u64, vp]
@@ -481,6 +483,10 @@ class ShardedContext:
         _check(lib().b200_sharded_prefix_reduce(self._ctx, _stream(stream), vt, op, local_size,
                                                 int(bool(exclusive)), int(bool(reverse)), _ptr(in_),
                                                 _ptr(out)))
+
+    def prefix_reduce_cyclic(self, vt, op, local_size, block_size, exclusive, in_, out, stream=None):
+        _check(lib().b200_sharded_prefix_reduce_cyclic(self._ctx, _stream(stream), vt, op, local_size,
+                                                       block_size, int(bool(exclusive)), _ptr(in_), _ptr(out)))
 
     def histogram(self, values, local_size, bucket_count, hist, before=None, stream=None):
         _check(lib().b200_sharded_histogram(self._ctx, _stream(stream), _ptr(values), local_size,

@@ -7,6 +7,22 @@
 
 namespace b200 {
 
+/// Block-cyclic whole-array scan over the GPUs of one box (sharded.cu): the global array
+/// is cut into blocks of 2^log2_block_tiles scan tiles, global block b lives on rank
+/// b % world as that rank's local block b / world.  Every rank runs ONE chained
+/// streaming scan over its local blocks; a block's tiles chain among themselves
+/// (block-relative prefixes), its last tile posts the block total {value, epoch} into the
+/// `table` of every rank (peer-mapped memory, one 16-byte store over NVLink), and its
+/// first tile turns the totals of all blocks in front of it (global order) into the
+/// block's offset, which it leaves in `blockoff` for the other tiles of the block.
+struct CyclicScan {
+    uint64_t *table[16];      // [rank]: that rank's table (local for rank == this rank)
+    uint64_t *blockoff;       // local: 2 words per round {value, epoch}
+    uint64_t *error;          // set when a wait for a peer times out
+    uint64_t epoch;
+    uint32_t rank, world, log2_block_tiles, table_stride; // entries per round in `table` (>= world)
+};
+
 struct ScanCall {
     cudaStream_t stream;
     const void *in;
@@ -18,6 +34,7 @@ struct ScanCall {
     void *carry_out;
     bool carry_api;    // whole array is one segment, optional carry
     const void *seeds = nullptr; // carry_api only: exclusive prefix of every 32 KiB tile (no look-back)
+    const CyclicScan *cyclic = nullptr; // carry_api only: block-cyclic multi-GPU scan
 };
 
 /// Tries the streaming kernels (power-of-two blocks up to a tile; whole-array

@@ -43,6 +43,10 @@
 #include <cstdio>
 #include <cstdlib>
 
+#ifndef B200_SCAN_LBW
+#define B200_SCAN_LBW 1
+#endif
+
 namespace b200 {
 
 template <int X> struct CLog2 { static constexpr int value = X <= 1 ? 0 : 1 + CLog2<X / 2>::value; };
@@ -63,7 +67,38 @@ struct FastParams {
     const void *carry_in;
     void *carry_out;
     const void *seeds;   // CHAIN: exclusive prefix per PHYSICAL tile, replaces the look-back
+    CyclicScan cyc;      // CHAIN: block-cyclic multi-GPU scan (world == 0: off)
 };
+
+/// 16-byte {value, epoch} entries exchanged between GPUs: one single-copy atomic
+/// 128-bit access at system scope, so a reader that sees the epoch sees its value
+B200_DEVICE void st_entry_sys(uint64_t *ptr, uint64_t value, uint64_t epoch) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.sys.global.b128 [%0], q;\n\t}"
+                 :: "l"(ptr), "l"(value), "l"(epoch) : "memory");
+}
+B200_DEVICE void ld_entry_sys(const uint64_t *ptr, uint64_t &value, uint64_t &epoch) {
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.sys.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(value), "=l"(epoch) : "l"(ptr) : "memory");
+}
+/// Wait (bounded: 20 s) until the entry carries `epoch`; false on time-out
+B200_DEVICE bool wait_entry_sys(const uint64_t *ptr, uint64_t epoch, uint64_t &value) {
+    uint64_t e, t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+        ld_entry_sys(ptr, value, e);
+        if (e == epoch)
+            return true;
+        if ((++spins & 255u) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > 20ull * 1000 * 1000 * 1000)
+                return false;
+        }
+        __nanosleep(64);
+    }
+}
 
 #if defined(B200_SCAN_TUNING)
 // development counters (accumulated in registers, flushed once per warp):
@@ -191,7 +226,7 @@ template <typename T, int Op, int J, int THREADS, bool FULL> struct TileScan {
 
 /// THREADS compute threads (+ one look-back warp when CHAIN), tiles of
 /// THREADS * J vectors, ring of S shared-memory slots.
-template <typename T, int Op, int J, int S, int THREADS, bool CHAIN, int LB>
+template <typename T, int Op, int J, int S, int THREADS, bool CHAIN, int LB, int LBW>
 __global__ void __launch_bounds__(THREADS + (CHAIN ? 32 + 32 * LB : 0),
                                   (THREADS >= 512 && (size_t) S * THREADS * J * 16 <= 112 * 1024) ? 2 : 1)
 scan_stream_kernel(const FastParams p) {
@@ -262,6 +297,63 @@ scan_stream_kernel(const FastParams p) {
             issue(i, atomicAdd(p.ticket, 1u));
     }
     __syncthreads();
+
+    // Exclusive prefix of `tile` within its segment by decoupled look-back (one warp)
+    auto look_back = [&](uint32_t tile) -> V {
+        V P = R::identity();
+        int64_t win = (int64_t) tile - 1;
+        bool done = false;
+        while (!done) {
+            // LBW windows of 32 preceding tiles each are fetched TOGETHER (their
+            // loads are independent: one L2 round trip, ~0.9 us under streaming
+            // load, covers 32 * LBW descriptors); lane 0 of window 0 is the
+            // nearest tile.  The windows are then examined nearest first.
+            // Polling competes with the stream for L2 bandwidth, so only lanes
+            // whose entry is still INVALID poll again, after a short back-off;
+            // entries beyond the nearest PREFIX are not needed at all.
+            V val[LBW];
+            uint32_t st[LBW];
+            #pragma unroll
+            for (int w = 0; w < LBW; ++w) {
+                const int64_t idx = win - 32 * w - lane;
+                val[w] = R::identity();
+                st[w] = DESC_PREFIX;
+                if (idx >= 0)
+                    st[w] = Desc<V>::observe(p.desc, (uint32_t) idx, val[w]);
+            }
+            DBG_ADD_LANE0(0, 1);
+            DBG_ADD_LANE0(1, 1);
+            #pragma unroll
+            for (int w = 0; w < LBW; ++w) {
+                if (done)
+                    break;
+                const int64_t idx = win - 32 * w - lane;
+                uint32_t pre;
+                while (true) {
+                    pre = __ballot_sync(FULL_MASK, st[w] == DESC_PREFIX);
+                    uint32_t inv = __ballot_sync(FULL_MASK, st[w] == DESC_INVALID);
+                    if (pre)
+                        inv &= (1u << (__ffs(pre) - 1)) - 1u;
+                    if (!inv)
+                        break;
+                    __nanosleep(100);
+                    if (st[w] == DESC_INVALID)
+                        st[w] = Desc<V>::observe(p.desc, (uint32_t) idx, val[w]);
+                    DBG_ADD_LANE0(1, 1);
+                }
+                if (pre) {
+                    const uint32_t stop = __ffs(pre) - 1;
+                    V contrib = lane <= stop ? val[w] : R::identity();
+                    P = R::apply(warp_reduce<V, Op>(contrib), P);
+                    done = true;
+                } else {
+                    P = R::apply(warp_reduce<V, Op>(val[w]), P);
+                }
+            }
+            win -= 32 * LBW;
+        }
+        return P;
+    };
 
     if constexpr (CHAIN) {
         // ---- two helper warps run ahead of the compute warps.
@@ -357,6 +449,22 @@ scan_stream_kernel(const FastParams p) {
                     DBG_ADD(8, DBG_CLOCK() - c1);
                 }
                 __syncwarp();
+                if (p.cyc.world) {
+                    // block-cyclic multi-GPU scan: the LAST tile of a block sends the block total
+                    // to every rank (one 16-byte store each).  This warp resolves the tile's prefix
+                    // within the block itself -- it never waits for another GPU, whereas the
+                    // look-back warps below do (block offsets): totals must not queue behind them.
+                    const uint32_t lbt = p.cyc.log2_block_tiles;
+                    if ((tile & ((1u << lbt) - 1u)) == (1u << lbt) - 1u) {
+                        const V rel = lbt ? look_back(tile) : R::identity();
+                        uint64_t bits = 0;
+                        const V agg = R::apply(rel, total);
+                        memcpy(&bits, &agg, sizeof(V));
+                        if (lane < p.cyc.world)
+                            st_entry_sys(p.cyc.table[lane] + 2 * ((size_t) (tile >> lbt) * p.cyc.table_stride + p.cyc.rank),
+                                         bits, p.cyc.epoch);
+                    }
+                }
             }
             if (lane == 0)
                 DBG_FLUSH();
@@ -388,44 +496,76 @@ scan_stream_kernel(const FastParams p) {
                     if (p.carry_in)
                         P = *(const V *) p.carry_in;
                 } else {
-                    int64_t win = (int64_t) tile - 1;
-                    while (true) {
-                        // window of the 32 preceding tiles; lane 0 is the nearest.
-                        // A poll is one L2 round trip (~0.9 us under streaming load)
-                        // and polling competes with the stream for L2 bandwidth, so
-                        // only lanes whose entry is still INVALID poll again, after
-                        // a short back-off; entries beyond the nearest PREFIX are
-                        // not needed at all.
-                        const int64_t idx = win - lane;
-                        V val = R::identity();
-                        uint32_t st = DESC_PREFIX, pre;
-                        if (idx >= 0)
-                            st = Desc<V>::observe(p.desc, (uint32_t) idx, val);
-                        DBG_ADD_LANE0(0, 1);
-                        DBG_ADD_LANE0(1, 1);
-                        while (true) {
-                            pre = __ballot_sync(FULL_MASK, st == DESC_PREFIX);
-                            uint32_t inv = __ballot_sync(FULL_MASK, st == DESC_INVALID);
-                            if (pre)
-                                inv &= (1u << (__ffs(pre) - 1)) - 1u;
-                            if (!inv)
-                                break;
-                            __nanosleep(100);
-                            if (st == DESC_INVALID)
-                                st = Desc<V>::observe(p.desc, (uint32_t) idx, val);
-                            DBG_ADD_LANE0(1, 1);
-                        }
-                        if (pre) {
-                            const uint32_t stop = __ffs(pre) - 1;
-                            V contrib = lane <= stop ? val : R::identity();
-                            P = R::apply(warp_reduce<V, Op>(contrib), P);
-                            break;
-                        }
-                        P = R::apply(warp_reduce<V, Op>(val), P);
-                        win -= 32;
-                    }
+                    P = look_back(tile);
                     if (lane == 0)
                         Desc<V>::publish(p.desc, tile, DESC_PREFIX, R::apply(P, total));
+                }
+                if (p.cyc.world) {
+                    // block-cyclic multi-GPU scan: P is relative to the block so far
+                    const uint32_t lbt = p.cyc.log2_block_tiles, W = p.cyc.world;
+                    const uint32_t j = tile >> lbt, i = tile & ((1u << lbt) - 1u);
+                    bool ok = true;
+                    // block offsets accumulate in double for float data (up to 4096 block totals
+                    // are chained: a float chain would lose the 1e-5 the single-GPU scan keeps)
+                    using A = typename std::conditional<std::is_same<V, float>::value, double, V>::type;
+                    using RA = Red<A, Op>;
+                    auto poll_blockoff = [&](uint32_t jj, uint64_t &bits) {
+                        uint64_t e = 0, t0 = 0;
+                        uint32_t spins = 0;
+                        while (true) {
+                            ld_relaxed_b128(p.cyc.blockoff + 2 * (size_t) jj, bits, e);
+                            if (e == p.cyc.epoch)
+                                return true;
+                            if ((++spins & 255u) == 0) {
+                                uint64_t now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                if (t0 == 0)
+                                    t0 = now;
+                                else if (now - t0 > 21ull * 1000 * 1000 * 1000)
+                                    return false;
+                            }
+                            __nanosleep(100);
+                        }
+                    };
+                    A off = RA::identity();
+                    if (i == 0) {
+                        // first tile: offset of block (j, rank) = offset of this rank's previous
+                        // block (+) the totals of the W blocks between the two in global order:
+                        // (j - 1, rank .. W - 1), then (j, 0 .. rank - 1) -- a fixed order
+                        uint64_t bits = 0;
+                        if (j > 0 && lane == 0) {
+                            ok &= poll_blockoff(j - 1, bits);
+                            memcpy(&off, &bits, sizeof(A));
+                        }
+                        const bool prev = lane >= p.cyc.rank; // this lane's entry belongs to round j - 1
+                        V v = R::identity();
+                        if (lane < W && (!prev || j > 0)) {
+                            const uint64_t *tab = p.cyc.table[p.cyc.rank];
+                            ok &= wait_entry_sys(tab + 2 * ((size_t) (prev ? j - 1 : j) * p.cyc.table_stride + lane),
+                                                 p.cyc.epoch, bits);
+                            memcpy(&v, &bits, sizeof(V));
+                        }
+                        if (j > 0) {
+                            for (uint32_t r = p.cyc.rank; r < W; ++r)
+                                off = RA::apply(off, (A) shfl_idx(v, (int) r));
+                        }
+                        for (uint32_t r = 0; r < p.cyc.rank; ++r)
+                            off = RA::apply(off, (A) shfl_idx(v, (int) r));
+                        if (lane == 0) {
+                            bits = 0;
+                            memcpy(&bits, &off, sizeof(A));
+                            st_relaxed_b128(p.cyc.blockoff + 2 * (size_t) j, bits, p.cyc.epoch);
+                        }
+                    } else {
+                        uint64_t bits = 0;
+                        if (lane == 0)
+                            ok &= poll_blockoff(j, bits);
+                        bits = __shfl_sync(FULL_MASK, bits, 0);
+                        memcpy(&off, &bits, sizeof(A));
+                    }
+                    if (!__all_sync(FULL_MASK, ok) && lane == 0)
+                        *p.cyc.error = 1;
+                    P = (V) RA::apply(off, (A) P);
                 }
                 if (lane == 0) {
                     s_prefix[m] = P;
@@ -607,17 +747,17 @@ template <typename K> static int prepare_kernel(K kernel, int threads, size_t sm
 // measured on B200 at 2^28 fp32, POW2 0.318 ms (6.7 TB/s) and CHAIN 0.38 ms
 // (5.6 TB/s).  256 x 4 with 6 slots: POW2 the same, CHAIN 0.44 ms; a second
 // look-back warp makes CHAIN slower (more polling, same dependency latency).
-template <int THREADS_, int J_, int S_, int LB_ = 2> struct Geom {
-    static constexpr int THREADS = THREADS_, J = J_, S = S_, LB = LB_;
+template <int THREADS_, int J_, int S_, int LB_ = 2, int LBW_ = 1> struct Geom {
+    static constexpr int THREADS = THREADS_, J = J_, S = S_, LB = LB_, LBW = LBW_;
 };
-using DefaultGeom = Geom<512, 4, 3, 1>;
+using DefaultGeom = Geom<512, 4, 3, 1, B200_SCAN_LBW>;
 
 template <typename T, int Op, bool CHAIN, typename G>
 static int launch_stream(const ScanCall &c, FastParams &p) {
     using V = typename ValueOf<T>::type;
     constexpr size_t SMEM = (size_t) G::S * G::THREADS * G::J * 16;
     constexpr int BLOCK = G::THREADS + (CHAIN ? 32 + 32 * G::LB : 0);
-    auto kernel = scan_stream_kernel<T, Op, G::J, G::S, G::THREADS, CHAIN, CHAIN ? G::LB : 0>;
+    auto kernel = scan_stream_kernel<T, Op, G::J, G::S, G::THREADS, CHAIN, CHAIN ? G::LB : 0, CHAIN ? G::LBW : 1>;
 
     // per device: opt in to the dynamic shared memory size, query residency
     static std::atomic<int> occ_cache[64];
@@ -679,7 +819,14 @@ template <typename T, int Op, typename G> static int launch_fast_g(const ScanCal
     }
 
     bool chain;
-    if (c.carry_api || c.bs >= c.size) {
+    if (c.cyclic) {
+        // every block of 2^log2_block_tiles tiles is a segment of the local chain
+        chain = true;
+        p.cyc = *c.cyclic;
+        p.seg_mask = (1u << c.cyclic->log2_block_tiles) - 1u;
+        if (c.reverse || c.seeds || (p.ntiles & p.seg_mask) != 0)
+            return fail(B200_ERR_INVALID, "block-cyclic scan: whole blocks, forward only!");
+    } else if (c.carry_api || c.bs >= c.size) {
         chain = true;
         p.seg_mask = 0xffffffffu;
     } else if (is_pow2(c.bs) && c.bs <= TILE) {
@@ -721,6 +868,12 @@ template <typename T, int Op> static int launch_fast(const ScanCall &c, bool *ha
             case 10: return launch_fast_g<T, Op, Geom<768, 4, 3, 1>>(c, handled);
             case 11: return launch_fast_g<T, Op, Geom<896, 4, 3, 1>>(c, handled);
             case 12: return launch_fast_g<T, Op, Geom<512, 6, 3, 1>>(c, handled);
+            case 13: return launch_fast_g<T, Op, Geom<512, 4, 3, 1, 2>>(c, handled);
+            case 14: return launch_fast_g<T, Op, Geom<512, 4, 3, 1, 4>>(c, handled);
+            case 15: return launch_fast_g<T, Op, Geom<512, 8, 3, 1, 2>>(c, handled);
+            case 16: return launch_fast_g<T, Op, Geom<512, 8, 3, 1, 4>>(c, handled);
+            case 17: return launch_fast_g<T, Op, Geom<512, 4, 3, 1, 8>>(c, handled);
+            case 18: return launch_fast_g<T, Op, Geom<512, 4, 6, 1, 4>>(c, handled);
             default: break;
         }
     }

@@ -31,6 +31,7 @@
 //              mailbox, wait, sum the W rows (optionally also the rows of the lower
 //              ranks = this rank's output offset per bucket).
 #include "common.cuh"
+#include "scan.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -41,6 +42,7 @@ namespace b200 {
 static constexpr uint32_t SH_MAX_WORLD = 16;
 static constexpr uint32_t SH_MAX_BUCKETS = 65536;  // histogram rows that fit the mailbox
 static constexpr uint64_t SH_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+static constexpr uint32_t SH_CYC_ROUNDS = 4096;    // blocks per rank of the block-cyclic scan
 
 /// Mailbox of one rank (device memory of that rank, mapped by every peer).
 /// [parity][sender]: a 16-byte {value, epoch} slot and a histogram row.
@@ -52,6 +54,9 @@ struct Mailbox {
     Slot scalar[2][SH_MAX_WORLD];
     Slot hist_flag[2][SH_MAX_WORLD];
     uint32_t hist[2][SH_MAX_WORLD][SH_MAX_BUCKETS];
+    // block-cyclic scan: {total, epoch} of block (round, sender); entries are told apart
+    // by the epoch of the call, so the table is never cleared
+    Slot cyc[SH_CYC_ROUNDS][SH_MAX_WORLD];
 };
 
 } // namespace b200
@@ -69,6 +74,7 @@ struct B200Sharded {
     uint64_t *scalars = nullptr; // [0] partial / total
     uint64_t *error = nullptr;   // pinned, mapped: set by a kernel whose wait for a peer timed out
     uint32_t *hist_local = nullptr; // SH_MAX_BUCKETS
+    uint64_t *blockoff = nullptr;   // block-cyclic scan: {offset, epoch} per local block
 };
 
 namespace b200 {
@@ -396,6 +402,10 @@ int b200_sharded_create(int rank, int world, B200Sharded **out) {
     if (err == cudaSuccess)
         err = cudaMalloc((void **) &c->hist_local, SH_MAX_BUCKETS * sizeof(uint32_t));
     if (err == cudaSuccess)
+        err = cudaMalloc((void **) &c->blockoff, SH_CYC_ROUNDS * 16);
+    if (err == cudaSuccess)
+        err = cudaMemset(c->blockoff, 0, SH_CYC_ROUNDS * 16);
+    if (err == cudaSuccess)
         err = cudaHostAlloc((void **) &c->error, 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (err == cudaSuccess) {
         memset(c->error, 0, 64);
@@ -449,6 +459,7 @@ int b200_sharded_destroy(B200Sharded *c) {
     cudaFree(c->mine);
     cudaFree(c->scalars);
     cudaFree(c->hist_local);
+    cudaFree(c->blockoff);
     if (c->error)
         cudaFreeHost(c->error);
     cudaFree(c->tsums);
@@ -523,6 +534,49 @@ int b200_sharded_prefix_reduce(B200Sharded *c, void *stream_, int vt, int op, ui
     if (local_size > 0)
         rc = b200_prefix_reduce_seeded(stream, vt, op, local_size, exclusive, reverse, in, out, c->seeds);
     return rc;
+}
+
+int b200_sharded_prefix_reduce_cyclic(B200Sharded *c, void *stream_, int vt, int op, uint64_t local_size,
+                                      uint64_t block_size, int exclusive, const void *in, void *out) {
+    int rc = check_ctx(c, "b200_sharded_prefix_reduce_cyclic()");
+    if (rc)
+        return rc;
+    const uint32_t tile = b200_scan_tile_elems(vt);
+    if (!seed_for(vt, op) || tile == 0)
+        return fail(B200_ERR_UNSUPPORTED,
+                    "b200_sharded_prefix_reduce_cyclic(): no existing kernel for type=%s, op=%s!", type_name(vt),
+                    op_name(op));
+    if (((uintptr_t) in | (uintptr_t) out) & 15)
+        return fail(B200_ERR_INVALID, "b200_sharded_prefix_reduce_cyclic(): the shard must be 16-byte aligned!");
+    if (block_size < tile || (block_size & (block_size - 1)) != 0 || local_size % block_size != 0 ||
+        local_size / block_size > SH_CYC_ROUNDS || local_size >= 0xffffffffull - 2 * tile)
+        return fail(B200_ERR_INVALID,
+                    "b200_sharded_prefix_reduce_cyclic(): blocks must be a power of two of at least %u elements, "
+                    "shards whole blocks (at most %u, fewer than 2^32 - 2^14 elements)!", tile, SH_CYC_ROUNDS);
+    if (local_size == 0)
+        return B200_OK;
+    cudaStream_t stream = resolve_stream(stream_);
+    c->epoch++;
+    CyclicScan cyc{};
+    for (int r = 0; r < c->world; ++r)
+        cyc.table[r] = (uint64_t *) &c->peers[r]->cyc[0][0];
+    cyc.blockoff = c->blockoff;
+    cyc.error = c->error;
+    cyc.epoch = c->epoch;
+    cyc.rank = (uint32_t) c->rank;
+    cyc.world = (uint32_t) c->world;
+    cyc.log2_block_tiles = log2i(block_size / tile);
+    cyc.table_stride = SH_MAX_WORLD;
+    ScanCall call{ stream, in, out, local_size, local_size, exclusive != 0, false, nullptr, nullptr, true };
+    call.cyclic = &cyc;
+    bool handled = false;
+    // (vt / op canonicalised like b200_block_prefix_reduce: signed add / and / or on the unsigned kernels)
+    rc = scan_fast_dispatch(vt, op, call, &handled);
+    if (rc)
+        return rc;
+    if (!handled)
+        return fail(B200_ERR_UNSUPPORTED, "b200_sharded_prefix_reduce_cyclic(): unsupported configuration");
+    return B200_OK;
 }
 
 int b200_sharded_histogram(B200Sharded *c, void *stream_, const uint32_t *values, uint64_t local_size,

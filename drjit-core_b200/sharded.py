@@ -210,6 +210,16 @@ class Sharded:
                                          local_out, carry, None)
 
     # -- mkperm histogram -------------------------------------------------------
+    def prefix_reduce_cyclic(self, vt, op, local_in, local_size, block_size, exclusive, local_out):
+        """Whole-array prefix reduction over a BLOCK-CYCLIC layout (global block b of
+        `block_size` elements lives on rank b % world as local block b // world): one pass
+        over the data instead of the two that contiguous shards need.  Peer mailboxes only
+        (b200_sharded_prefix_reduce_cyclic, csrc/sharded.cu)."""
+        if self.peer is None:
+            raise RuntimeError("sharded prefix_reduce_cyclic(): needs the peer-mailbox exchange "
+                               "(CUDA, mailboxes mapped on every rank)")
+        self.peer.prefix_reduce_cyclic(vt, op, local_size, block_size, exclusive, local_in, local_out)
+
     def mkperm_histogram(self, local_values, local_size, bucket_count, want_offsets=False):
         """Global per-bucket counts (int32 tensor of bucket_count entries on every
         rank).  With want_offsets also returns this rank's exclusive offset per

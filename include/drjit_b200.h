@@ -361,6 +361,18 @@ B200_API int b200_sharded_prefix_reduce(B200Sharded *ctx, void *stream, int vt, 
                                         uint64_t local_size, int exclusive, int reverse,
                                         const void *in, void *out);
 
+/* The same prefix reduction over a BLOCK-CYCLIC layout (opt-in): the global array is cut
+ * into blocks of `block_size` elements (a power of two, at least one 32 KiB scan tile),
+ * global block b lives on rank b % world as local block b / world; local_size: elements
+ * of this rank (whole blocks, the same on every rank).  ONE pass over the data (8 B /
+ * element per GPU, against 12 for contiguous shards, where a rank cannot start before it
+ * knows the totals of all ranks in front of it): every rank runs one chained streaming
+ * scan, block totals travel as single 16-byte stores into peer-mapped tables.  Forward
+ * only, no float16. */
+B200_API int b200_sharded_prefix_reduce_cyclic(B200Sharded *ctx, void *stream, int vt, int op,
+                                               uint64_t local_size, uint64_t block_size,
+                                               int exclusive, const void *in, void *out);
+
 /* Global bucket counts of mkperm keys (phase 1 of jit_block_mkperm over the sharded
  * array): hist[bucket_count] on every rank; `before` (may be NULL) receives the
  * counts of the ranks in front of this one, i.e. this rank's first output slot

@@ -80,6 +80,38 @@ def main():
                                 ref = O.block_prefix_reduce(vt, op, x, total, excl, rev)[start:start + n_local]
                                 if not np.array_equal(got, ref):
                                     bad.append((exchange, "scan", tname, opn, total, excl, rev))
+        # ---- block-cyclic layout (peer exchange only): global block b lives on rank b % world;
+        # one chained pass, block totals through the peer-mapped tables
+        if exchange == "peer":
+            for tname, gen, block in (("u32", u32_input, 8192), ("f32", f32_input, 16384), ("u64", u64_input, 4096),
+                                      ("u32", u32_input, 1 << 18)):
+                vt = VT[tname]
+                dt = oracle.NP_OF_VT[vt]
+                for rounds in (1, 5, 16):
+                    n_local = rounds * block
+                    total = n_local * world
+                    x = gen(total)
+                    mine = np.concatenate([x[(j * world + rank) * block:(j * world + rank + 1) * block]
+                                           for j in range(rounds)])
+                    d_x = to_dev(mine)
+                    for excl in (1, 0):
+                        d_out = torch.empty_like(d_x)
+                        sh.prefix_reduce_cyclic(vt, OP["add"], d_x, n_local, block, bool(excl), d_out)
+                        torch.cuda.synchronize()
+                        got = d_out.cpu().numpy().view(dt)
+                        if tname == "f32":
+                            x64 = x.astype(np.float64)
+                            full = np.cumsum(x64) - (x64 if excl else 0)
+                        else:
+                            full = O.block_prefix_reduce(vt, OP["add"], x, total, excl, 0)
+                        ref = np.concatenate([full[(j * world + rank) * block:(j * world + rank + 1) * block]
+                                              for j in range(rounds)])
+                        if tname == "f32":
+                            err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))
+                            if err > 1e-5:  # fp32 Add: 1e-5 relative against fp64
+                                bad.append(("cyclic", tname, block, rounds, excl, float(err)))
+                        elif not np.array_equal(got, ref):
+                            bad.append(("cyclic", tname, block, rounds, excl))
         # ---- mkperm histogram (+ this rank's offsets inside every bucket)
         for total, buckets in ((100003, 16), ((1 << 21) + 5, 1024), ((1 << 21) + 5, 65536)):
             start, n_local = sharded.shard_bounds(total, world, rank)
