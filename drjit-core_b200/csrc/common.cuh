@@ -59,8 +59,8 @@ void *temp_alloc(size_t bytes, cudaStream_t stream);
 void temp_free(void *ptr, cudaStream_t stream);
 /// A pinned (device-accessible) host word owned by the calling thread, or NULL
 uint32_t *pinned_scalar();
-/// A zero-initialised device word that belongs to (current device, stream): kernels
-/// on that stream use it as a "last CTA done" ticket counter and leave it at zero
+/// TWO zero-initialised device words that belong to (current device, stream): kernels
+/// on that stream use them as ticket / "last CTA done" counters and leave them at zero
 /// again, so consecutive launches (in-order on the stream, also when replayed from a
 /// graph captured on it) need no memset.  NULL when the table is full.
 unsigned int *stream_ticket(cudaStream_t stream);

@@ -19,6 +19,8 @@
 //           (run-to-run deterministic, also for floating point).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b200 {
 
 static constexpr int REDUCE_THREADS = 256;
@@ -420,13 +422,42 @@ reduce_chunks_kernel(const T *__restrict__ in, void *__restrict__ out_, uint64_t
             __threadfence();
             const V *partials = (const V *) out_;
             const uint32_t lane = threadIdx.x & 31;
-            for (uint64_t b = threadIdx.x >> 5; b < nblocks; b += REDUCE_THREADS / 32) {
-                V acc = R::identity();
-                for (uint32_t i = lane; i < chunks_per_block; i += 32)
-                    acc = R::apply(acc, __ldcg(partials + b * chunks_per_block + i));
-                acc = warp_reduce<V, Op>(acc);
+            if (nblocks == 1) {
+                // the whole CTA on one block: thread t takes the partials t, t + 256, ... (four
+                // independent loads in flight), then the usual warp / CTA tree
+                V a4[4] = { R::identity(), R::identity(), R::identity(), R::identity() };
+                uint32_t i = threadIdx.x;
+                for (; i + 3 * REDUCE_THREADS < chunks_per_block; i += 4 * REDUCE_THREADS) {
+                    V v[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = __ldcg(partials + i + u * REDUCE_THREADS);
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        a4[u] = R::apply(a4[u], v[u]);
+                }
+                for (; i < chunks_per_block; i += REDUCE_THREADS)
+                    a4[0] = R::apply(a4[0], __ldcg(partials + i));
+                V acc = warp_reduce<V, Op>(R::apply(R::apply(a4[0], a4[1]), R::apply(a4[2], a4[3])));
+                __syncthreads(); // warp_part reuse
                 if (lane == 0)
-                    final_out[b] = from_value<T>(acc);
+                    warp_part[threadIdx.x >> 5] = acc;
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    acc = threadIdx.x < REDUCE_THREADS / 32 ? warp_part[threadIdx.x] : R::identity();
+                    acc = warp_reduce<V, Op>(acc);
+                    if (threadIdx.x == 0)
+                        final_out[0] = from_value<T>(acc);
+                }
+            } else {
+                for (uint64_t b = threadIdx.x >> 5; b < nblocks; b += REDUCE_THREADS / 32) {
+                    V acc = R::identity();
+                    for (uint32_t i = lane; i < chunks_per_block; i += 32)
+                        acc = R::apply(acc, __ldcg(partials + b * chunks_per_block + i));
+                    acc = warp_reduce<V, Op>(acc);
+                    if (lane == 0)
+                        final_out[b] = from_value<T>(acc);
+                }
             }
             if (threadIdx.x == 0)
                 *ticket = 0;
@@ -606,7 +637,8 @@ template <typename T, int Op> static int launch_block_reduce(const ReduceCall &c
         return fail(B200_ERR_CUDA, "jit_block_reduce(): out of memory (%zu bytes)",
                     (size_t) (nteams * sizeof(V)));
     // few blocks: one launch, the last CTA finishes (no second kernel in the stream)
-    unsigned int *ticket = nblocks <= 64 ? stream_ticket(c.stream) : nullptr;
+    static const bool two_launches = getenv("B200_REDUCE_TWO_LAUNCHES") != nullptr; // (development switch)
+    unsigned int *ticket = nblocks <= 64 && !two_launches ? stream_ticket(c.stream) : nullptr;
     if (ticket) {
         reduce_chunks_kernel<T, Op, REDUCE_THREADS, true, U><<<grid, REDUCE_THREADS, 0, c.stream>>>(
             in, partials, size, bs, chunk, (uint32_t) chunks, nteams, ticket, out, nblocks);

@@ -231,7 +231,7 @@ void temp_free(void *ptr, cudaStream_t stream) {
         cudaFreeAsync(ptr, stream);
 }
 
-// One ticket word per (device, stream), handed out from a per-device block of device
+// Two ticket words per (device, stream), handed out from a per-device block of device
 // memory that is zeroed once.
 unsigned int *stream_ticket(cudaStream_t stream) {
     constexpr int SLOTS = 1024;
@@ -247,8 +247,8 @@ unsigned int *stream_ticket(cudaStream_t stream) {
         tables.resize(dev + 1);
     Table &t = tables[dev];
     if (!t.words) {
-        if (cudaMalloc((void **) &t.words, SLOTS * sizeof(unsigned int)) != cudaSuccess ||
-            cudaMemset(t.words, 0, SLOTS * sizeof(unsigned int)) != cudaSuccess) {
+        if (cudaMalloc((void **) &t.words, SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(t.words, 0, SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess) {
             cudaGetLastError();
             t.words = nullptr;
             return nullptr;
@@ -256,11 +256,11 @@ unsigned int *stream_ticket(cudaStream_t stream) {
     }
     for (size_t i = 0; i < t.owners.size(); ++i)
         if (t.owners[i] == stream)
-            return t.words + i;
+            return t.words + 2 * i;
     if ((int) t.owners.size() == SLOTS)
         return nullptr;
     t.owners.push_back(stream);
-    return t.words + (t.owners.size() - 1);
+    return t.words + 2 * (t.owners.size() - 1);
 }
 
 // One pinned host word per calling thread.  Kernels of the synchronising entry

@@ -64,6 +64,7 @@ struct FastParams {
     uint32_t debug;      // development switches
     uint64_t *desc;      // CHAIN: ntiles descriptors (zero-initialised)
     uint32_t *ticket;    // tile ticket counter (zero-initialised)
+    uint32_t *done;      // optional: CTAs that have finished; the last one zeroes both counters
     const void *carry_in;
     void *carry_out;
     const void *seeds;   // CHAIN: exclusive prefix per PHYSICAL tile, replaces the look-back
@@ -710,6 +711,14 @@ scan_stream_kernel(const FastParams p) {
             }
         }
     }
+    if (tid == 0 && p.done) {
+        // per-stream counters (no memset per call): the CTA that finishes last leaves them at zero
+        __threadfence();
+        if (atomicAdd(p.done, 1u) == gridDim.x - 1) {
+            *p.ticket = 0;
+            *p.done = 0;
+        }
+    }
     if (tid == 32)
         DBG_ADD(10, DBG_CLOCK() - loop0);
     if (tid == 0 || tid == 32)
@@ -773,7 +782,12 @@ static int launch_stream(const ScanCall &c, FastParams &p) {
     }
 
     void *scratch = nullptr;
-    {
+    unsigned int *counters = CHAIN ? nullptr : stream_ticket(c.stream);
+    if (counters) {
+        // independent tiles: only the ticket is needed -- the stream's own self-resetting counters
+        p.ticket = counters;
+        p.done = counters + 1;
+    } else {
         size_t desc_bytes = CHAIN ? (size_t) p.ntiles * Desc<V>::WORDS * sizeof(uint64_t) : 0;
         scratch = temp_alloc(desc_bytes + 16, c.stream);
         if (!scratch)
