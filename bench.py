@@ -551,8 +551,26 @@ def measure_e2e(torch, dr, dist, world, dev, n, n_global, calls, call, out_elems
     return {"value": world * len(calls) * n / (ms_step * 1e-3), "unit": "elements/s",
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_step,
             "pcie_GBs": (h2d + d2h) / (ms_step * 1e-3) / 1e9,
+            "host": host_topology(),
             "note": "pinned host input -> H2D -> 28 C-ABI calls -> D2H of every result "
-                    "(copy stream overlapped with the kernels); PCIe bound"}
+                    "(copy stream overlapped with the kernels); PCIe bound.  pcie_GBs is PER RANK; at N > 1 "
+                    "the ranks share the host's memory system (the 8-GPU boxes of this pool expose ONE NUMA "
+                    "node with 32 cores to all GPUs -- profiles/r2_topo_n8.txt -- so there is nothing to bind "
+                    "a rank to: the aggregate of ~96 GB/s is the host's limit)"}
+
+
+def host_topology():
+    """CPUs and NUMA nodes the process can see (evidence for the e2e figure at N > 1)."""
+    nodes = 0
+    try:
+        nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except OSError:
+        pass
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = os.cpu_count()
+    return {"cpus": cpus, "numa_nodes": nodes}
 
 
 def time_call(torch, fn, iters=5, warmup=2):

@@ -177,9 +177,23 @@ shard_scan_seed_kernel(const PeerTable peers, Mailbox *mine, uint32_t rank, uint
     const uint32_t l0 = min(tid * per, ntiles), l1 = min(l0 + per, ntiles);
     auto phys = [&](uint32_t l) { return reverse ? ntiles - 1 - l : l; };
 
+    // (eight independent loads in flight: a dependent load per step would cost one L2 round
+    // trip per tile sum -- 64 of them per thread for a 2 GiB shard)
     V local = R::identity();
-    for (uint32_t l = l0; l < l1; ++l)
-        local = R::apply(local, tsums[phys(l)]);
+    {
+        uint32_t l = l0;
+        for (; l + 8 <= l1; l += 8) {
+            V v[8];
+            #pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = __ldg(tsums + phys(l + u));
+            #pragma unroll
+            for (int u = 0; u < 8; ++u)
+                local = R::apply(local, v[u]);
+        }
+        for (; l < l1; ++l)
+            local = R::apply(local, __ldg(tsums + phys(l)));
+    }
     // block-wide inclusive scan of the thread totals (fixed order)
     V incl = local;
     #pragma unroll
@@ -232,10 +246,24 @@ shard_scan_seed_kernel(const PeerTable peers, Mailbox *mine, uint32_t rank, uint
     if (!s_ok)
         return;
     V run = R::apply(s_carry, excl);
-    for (uint32_t l = l0; l < l1; ++l) {
-        const uint32_t p = phys(l);
-        seeds[p] = run;
-        run = R::apply(run, tsums[p]);
+    {
+        uint32_t l = l0;
+        for (; l + 8 <= l1; l += 8) {
+            V v[8];
+            #pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = __ldg(tsums + phys(l + u));
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                seeds[phys(l + u)] = run;
+                run = R::apply(run, v[u]);
+            }
+        }
+        for (; l < l1; ++l) {
+            const uint32_t p = phys(l);
+            seeds[p] = run;
+            run = R::apply(run, __ldg(tsums + p));
+        }
     }
 }
 
