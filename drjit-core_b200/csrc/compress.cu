@@ -227,6 +227,7 @@ static constexpr uint32_t CT_TILE = CT_WARPS * CT_WARP_ENTRIES;     // 32768 ent
 struct __align__(16) CtBits { uint32_t w[CT_ROWS / 2]; };            // a thread's bits: rows 2q | 2q + 1 << 16
 static constexpr uint32_t CT_SPARSE = 48;                           // set entries per 512-entry row
 static constexpr uint32_t CT_STAGE = 2 * 512 + 4;                   // staging words per warp (two rows)
+static constexpr uint32_t CT_LOCAL = 1024;                          // a sparse tile's indices fit its 4 KiB of bits
 static constexpr uint32_t CT_GROUP_SHIFT = 7;                       // 128 tiles per counter group
 static_assert((1u << CT_GROUP_SHIFT) <= CT_THREADS, "one tile count per thread");
 
@@ -242,6 +243,60 @@ B200_DEVICE uint32_t pack16(uint4 v) {
     return pack4(v.x) | (pack4(v.y) << 4) | (pack4(v.z) << 8) | (pack4(v.w) << 12);
 }
 
+/// Inclusive scans over the lanes of all CT_ROWS row counts at once: three 10-bit
+/// fields per register (a row holds at most 512 set entries).  c[j]: set entries of
+/// this lane's word of row j, P: packed inclusive scans, T: packed row totals.
+struct CtScan {
+    static constexpr int J = CT_ROWS, NP = (J + 2) / 3;
+    uint32_t c[J], P[NP], T[NP];
+    B200_DEVICE uint32_t incl(int j) const { return (P[j / 3] >> (10 * (j % 3))) & 0x3ffu; }
+    B200_DEVICE uint32_t total(int j) const { return (T[j / 3] >> (10 * (j % 3))) & 0x3ffu; }
+    B200_DEVICE void run(const uint32_t (&hp)[CT_ROWS / 2], uint32_t lane) {
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            c[j] = __popc((hp[j / 2] >> (16 * (j & 1))) & 0xffffu);
+        #pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            P[i] = 0;
+            #pragma unroll
+            for (int f = 0; f < 3; ++f)
+                if (i * 3 + f < J)
+                    P[i] |= c[i * 3 + f] << (10 * f);
+        }
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            #pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const uint32_t up = __shfl_up_sync(FULL_MASK, P[i], d);
+                if (lane >= (uint32_t) d)
+                    P[i] += up;
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < NP; ++i)
+            T[i] = __shfl_sync(FULL_MASK, P[i], 31);
+    }
+};
+
+/// Sparse expansion of a warp's 4096 entries: every lane walks the set bits of its
+/// own words and stores the entry indices (item0 = index of bit 0 of this lane's word
+/// of row 0) to out[first ..] in ascending order.
+B200_DEVICE void ct_walk_scanned(const uint32_t (&hp)[CT_ROWS / 2], const CtScan &sc, uint32_t first,
+                                 uint32_t item0, uint32_t *__restrict__ out) {
+    uint32_t row_first = first;
+    #pragma unroll
+    for (int j = 0; j < CT_ROWS; ++j) {
+        uint32_t word = (hp[j / 2] >> (16 * (j & 1))) & 0xffffu;
+        uint32_t o = row_first + sc.incl(j) - sc.c[j]; // slot of this lane's first set entry
+        while (word) {
+            const uint32_t b = __ffs(word) - 1;
+            word &= word - 1;
+            out[o++] = item0 + j * 512 + b;
+        }
+        row_first += sc.total(j);
+    }
+}
+
 /// Virtual layout: entry i of the mask is byte (i + mis) of the 16-byte aligned
 /// array (in - mis); bits / tiles are indexed in that virtual space.
 __global__ void __launch_bounds__(CT_THREADS)
@@ -249,6 +304,7 @@ compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis
                      CtBits *__restrict__ bits, uint32_t *__restrict__ counts,
                      uint32_t *__restrict__ group_counts) {
     __shared__ uint32_t s_cnt[CT_WARPS];
+    __shared__ __align__(16) uint16_t s_tr[CT_WARPS][CT_ROWS * 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *vin = in - mis;
     const uint64_t vend = size + mis; // valid virtual bytes: [mis, vend)
@@ -284,18 +340,60 @@ compress_pack_kernel(const uint8_t *__restrict__ in, uint64_t size, uint32_t mis
         hp.w[q] = pack16(v[2 * q]) | (pack16(v[2 * q + 1]) << 16);
         pc += __popc(hp.w[q]);
     }
-    bits[(size_t) blockIdx.x * CT_THREADS + tid] = hp;
     const uint32_t c = __reduce_add_sync(FULL_MASK, pc);
     if (lane == 0)
         s_cnt[warp] = c;
     __syncthreads();
+    uint32_t t = 0, first = 0; // set entries of the tile / in front of this warp
+    #pragma unroll
+    for (int w = 0; w < CT_WARPS; ++w) {
+        const uint32_t cw = s_cnt[w];
+        t += cw;
+        first += (uint32_t) w < warp ? cw : 0u;
+    }
     if (tid == 0) {
-        uint32_t t = 0;
-        #pragma unroll
-        for (int w = 0; w < CT_WARPS; ++w)
-            t += s_cnt[w];
         counts[blockIdx.x] = t;
-        atomicAdd(group_counts + (blockIdx.x >> CT_GROUP_SHIFT), t);
+        if (t)
+            atomicAdd(group_counts + (blockIdx.x >> CT_GROUP_SHIFT), t);
+    }
+    if (t == 0)
+        return; // (nothing will look at this tile's slot)
+    if (t > CT_LOCAL) {
+        bits[(size_t) blockIdx.x * CT_THREADS + tid] = hp;
+        return;
+    }
+    // ---- sparse tile: its <= CT_LOCAL indices go, in order, where its bits would have
+    // gone (the expand kernel then only moves them to their final place).  The warp's
+    // 256 half words are transposed through shared memory so that lane l holds the 128
+    // CONSECUTIVE entries [128 l, 128 l + 128) of the warp's 4096: one lane scan instead
+    // of one per row.
+    if (c == 0)
+        return; // warp-uniform
+    uint16_t *tr = s_tr[warp];
+    #pragma unroll
+    for (int j = 0; j < CT_ROWS; ++j)
+        tr[j * 32 + lane] = (uint16_t) (hp.w[j / 2] >> (16 * (j & 1)));
+    __syncwarp();
+    const uint4 w4 = ((const uint4 *) tr)[lane];
+    const uint32_t w[4] = { w4.x, w4.y, w4.z, w4.w };
+    const uint32_t mine = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+    uint32_t incl = mine;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= (uint32_t) d)
+            incl += up;
+    }
+    uint32_t *slot = (uint32_t *) (bits + (size_t) blockIdx.x * CT_THREADS) + first + incl - mine;
+    const uint32_t item0 = (uint32_t) blockIdx.x * CT_TILE + warp * CT_WARP_ENTRIES + lane * 128 - mis;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t word = w[k];
+        while (word) {
+            const uint32_t b = __ffs(word) - 1;
+            word &= word - 1;
+            *slot++ = item0 + k * 32 + b;
+        }
     }
 }
 
@@ -309,6 +407,10 @@ compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restri
     const uint32_t tile = blockIdx.x;
     uint32_t *stage = ct_stage + warp * CT_STAGE;
 
+    // the tile's count, its slot (bits, or -- sparse tiles, expanded by the pack kernel
+    // already -- up to CT_LOCAL indices) and the counters in front of it are requested
+    // together: one memory round trip per CTA
+    const uint32_t tcount = __ldg(counts + tile);
     uint32_t hp[CT_ROWS / 2];
     {
         const uint4 raw = __ldg((const uint4 *) (bits + (size_t) tile * CT_THREADS + tid));
@@ -327,38 +429,19 @@ compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restri
         before = __reduce_add_sync(FULL_MASK, before);
     }
 
-    // inclusive scans over the lanes of all row counts at once: three 10-bit
-    // fields per register (a row holds at most 512 set entries)
-    constexpr int J = CT_ROWS, NP = (J + 2) / 3;
-    uint32_t c[J], P[NP];
-    #pragma unroll
-    for (int j = 0; j < J; ++j)
-        c[j] = __popc((hp[j / 2] >> (16 * (j & 1))) & 0xffffu);
-    #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        P[i] = 0;
-        #pragma unroll
-        for (int f = 0; f < 3; ++f)
-            if (i * 3 + f < J)
-                P[i] |= c[i * 3 + f] << (10 * f);
-    }
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            const uint32_t up = __shfl_up_sync(FULL_MASK, P[i], d);
-            if (lane >= (uint32_t) d)
-                P[i] += up;
-        }
-    }
-    uint32_t T[NP];
-    #pragma unroll
-    for (int i = 0; i < NP; ++i)
-        T[i] = __shfl_sync(FULL_MASK, P[i], 31);
+    // tiles without set entries have nothing to do (the last tile leaves the count)
+    if (tcount == 0 && tile != ntiles - 1)
+        return;
+    const bool local = tcount <= CT_LOCAL;
+    constexpr int J = CT_ROWS;
+    CtScan sc;
     uint32_t wtotal = 0;
-    #pragma unroll
-    for (int j = 0; j < J; ++j)
-        wtotal += (T[j / 3] >> (10 * (j % 3))) & 0x3ffu;
+    if (!local) {
+        sc.run(hp, lane);
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            wtotal += sc.total(j);
+    }
     if (lane == 0) {
         s_wtot[warp] = wtotal;
         s_before[warp] = before;
@@ -370,6 +453,15 @@ compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restri
         first += s_before[w] + ((uint32_t) w < warp ? s_wtot[w] : 0u);
         tile_total += s_wtot[w];
     }
+    if (local) { // (block-uniform) first = everything in front of the tile
+        if (tile == ntiles - 1 && tid == 0)
+            *count_out = first + tcount;
+        #pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+            if (4 * tid + k < tcount)
+                out[first + 4 * tid + k] = hp[k];
+        return;
+    }
     if (tile == ntiles - 1 && tid == 0)
         *count_out = first + tile_total; // warp 0: first = everything in front of the tile
 
@@ -380,19 +472,7 @@ compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restri
         return; // warp-uniform
     if (wtotal <= CT_SPARSE * J) {
         // sparse: every lane walks its own set bits and stores straight to global
-        uint32_t row_first = first;
-        #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const uint32_t incl = (P[j / 3] >> (10 * (j % 3))) & 0x3ffu;
-            uint32_t word = (hp[j / 2] >> (16 * (j & 1))) & 0xffffu;
-            uint32_t o = row_first + incl - c[j]; // slot of this lane's first set entry
-            while (word) {
-                const uint32_t b = __ffs(word) - 1;
-                word &= word - 1;
-                out[o++] = item0 + j * 512 + b;
-            }
-            row_first += (T[j / 3] >> (10 * (j % 3))) & 0x3ffu;
-        }
+        ct_walk_scanned(hp, sc, first, item0, out);
         return;
     }
 
@@ -402,8 +482,8 @@ compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restri
     uint32_t pair_first = first;
     #pragma unroll
     for (int q = 0; q < J / 2; ++q) {
-        const uint32_t t0 = (T[(2 * q) / 3] >> (10 * ((2 * q) % 3))) & 0x3ffu;
-        const uint32_t t1 = (T[(2 * q + 1) / 3] >> (10 * ((2 * q + 1) % 3))) & 0x3ffu;
+        const uint32_t t0 = sc.total(2 * q);
+        const uint32_t t1 = sc.total(2 * q + 1);
         const uint32_t pair_total = t0 + t1;
         if (pair_total == 0)
             continue; // warp-uniform
@@ -423,10 +503,10 @@ compress_expand_kernel(const CtBits *__restrict__ bits, const uint32_t *__restri
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int j = 2 * q + r;
-            const uint32_t incl = (P[j / 3] >> (10 * (j % 3))) & 0x3ffu;
+            const uint32_t incl = sc.incl(j);
             const uint32_t word = (hp[j / 2] >> (16 * (j & 1))) & 0xffffu;
             const uint32_t lane_base =
-                (uint32_t) __cvta_generic_to_shared(stage + a + (r ? t0 : 0u) + (incl - c[j]));
+                (uint32_t) __cvta_generic_to_shared(stage + a + (r ? t0 : 0u) + (incl - sc.c[j]));
             if (!rotated) {
                 uint32_t sp = lane_base, v = item0 + j * 512;
                 #pragma unroll

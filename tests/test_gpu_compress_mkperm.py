@@ -91,6 +91,39 @@ def test_compress_misaligned_output_and_density_sweep(dr, O):
     assert not bad, bad
 
 
+def test_compress_mixed_tile_kinds(dr, O):
+    # tiles of 32768 entries: empty ones, sparse ones (<= 1024 set entries: expanded by the
+    # pack kernel into the tile's own bit slot), tiles just above that threshold and dense
+    # ones, in one mask; every input / output alignment; the last tile empty or sparse
+    rng = np.random.default_rng(7)
+    bad = []
+    for ntiles, tail in ((37, 0), (64, 777), (130, 32767), (300, 5)):
+        size = ntiles * 32768 + tail
+        m = np.zeros(size, dtype=np.uint8)
+        for t in range(ntiles + 1):
+            lo, hi = t * 32768, min((t + 1) * 32768, size)
+            if hi <= lo:
+                continue
+            kind = t % 6
+            want = (0, 1, 1024, 1025, 3000, hi - lo)[kind]
+            want = min(want, hi - lo)
+            if t == ntiles:
+                want = min(3, hi - lo) if ntiles % 2 else 0
+            if want:
+                m[lo + rng.choice(hi - lo, size=want, replace=False)] = 1
+        ridx, rcnt = O.compress(m)
+        for off_in, off_out in ((0, 0), (5, 1), (11, 3)):
+            d_in = to_dev(m, off_in)
+            d_out = empty_dev(size + 8, np.uint32, off_out)
+            d_out.fill_(-1)
+            cnt = dr.jit_compress(CUDA, d_in, size, d_out)
+            got = to_host(d_out, np.uint32)
+            if cnt != rcnt or not np.array_equal(got[:cnt], ridx) or \
+               not np.all(got[cnt:cnt + 8] == 0xffffffff):
+                bad.append((ntiles, tail, off_in, off_out, cnt, rcnt))
+    assert not bad, bad
+
+
 def test_compress_full_size(dr, O):
     # BASELINE.json configs[2]: 2^28-element mask at densities 0.01 / 0.5 / 0.99
     n = 1 << 28

@@ -74,7 +74,8 @@ def main():
         ms = timeit(lambda: dr.jit_reduce_dot(CUDA, F32, x, out, n, oi))
         report("dot f32", ms, 8 * n)
 
-    for d in (0.01, 0.5, 0.99) if on("compress") else []:
+    dens = (0.001, 0.01, 0.03, 0.05, 0.1, 0.5, 0.99) if "compress_sweep" in want else (0.01, 0.5, 0.99)
+    for d in dens if on("compress") or "compress_sweep" in want else []:
         m = (torch.rand(n, device="cuda") < d).to(torch.uint8)
         cnt = int(m.sum().item())
         ms = timeit(lambda: dr.jit_compress(CUDA, m, n, oi))
