@@ -552,8 +552,11 @@ template <int IN, uint32_t TILE>
 __global__ void __launch_bounds__(MT_THREADS)
 mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, const TileGeom g,
                         uint32_t shift, uint32_t mask, uint32_t kmax, uint32_t bins,
-                        uint32_t *__restrict__ table) {
+                        uint32_t halves, uint32_t *__restrict__ table) {
     constexpr uint32_t HALFK = TILE / 2;
+    // halves == 1 (wide-digit ranking): the two halves of a tile share a histogram and
+    // the table is [group][digit][tile]
+    const uint32_t hshift = halves == 2 ? 0u : 1u;
     constexpr int V = HALFK / 4 / MT_THREADS, U = 8 / V; // 16-byte loads per half, halves per step
     static_assert(V >= 1 && MT_GROUP % U == 0, "eight 16-byte loads in flight per thread");
     extern __shared__ uint32_t mk_smem[];
@@ -588,7 +591,7 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, const TileGeom g,
         }
         #pragma unroll
         for (int u = 0; u < U; ++u) {
-            uint32_t *h = mk_smem + (t + u) * bins;
+            uint32_t *h = mk_smem + ((t + u) >> hshift) * bins;
             if (full[u]) {
                 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -604,10 +607,14 @@ mkperm_tile_hist_kernel(const uint32_t *__restrict__ keys, const TileGeom g,
         }
     }
     __syncthreads();
-    for (uint32_t i = tid; i < MT_GROUP * bins; i += MT_THREADS) {
-        const uint32_t d = i / MT_GROUP, t = i % MT_GROUP;
-        if (tile0 + t / 2 < g.ntiles)
-            table[table_index(g, tile0 + t / 2, d, bins) + (t & 1)] = mk_smem[t * bins + d];
+    const uint32_t nslots = MT_GROUP >> hshift;
+    for (uint32_t i = tid; i < nslots * bins; i += MT_THREADS) {
+        const uint32_t d = i / nslots, t = i % nslots;
+        const uint32_t tile = tile0 + ((t << hshift) >> 1);
+        if (tile < g.ntiles) {
+            const uint64_t at = table_index(g, tile, d, bins);
+            table[hshift ? at >> 1 : at + (t & 1)] = mk_smem[t * bins + d];
+        }
     }
 }
 
@@ -650,6 +657,7 @@ struct RkArgs {
     TileGeom geom;
     uint32_t shift, mask, bins, width, ib, kmax, index_base;
     uint32_t *out0, *out1;
+    uint32_t halves; // count table entries per (digit, tile): 2 (6-bit ranking kernel) or 1 (wide digits)
 };
 
 /// Staging slot of run r (sorted-tile slot `ls`, first global slot at word address
@@ -987,6 +995,253 @@ static cudaError_t rk_launch(cudaStream_t stream, int bits, int in, int out, con
     return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------- single sorting group: ranked tiles, wide digits
+//
+// 7- and 8-bit digits: thread-private counters (above) would need 256 digits x 512
+// threads x 2 bytes.  Here the counters are private to a WARP (16 x 256 words), and
+// the order of equal digits inside one warp step -- which a plain atomic counter
+// would leave to the hardware -- is made explicit: every lane ORs its lane bit into
+// the step's match word of its digit (atoms.or: 5 issue cycles when the lanes
+// disagree, against 256 for match.any, tools/ubench_warp_ops.cu), reads the word
+// back and ranks itself by the number of lower lanes in it; the first lane of every
+// digit adds the group to the warp's counter and clears the word.  A warp walks its
+// 512 keys in 16 such steps (step i, lane l <-> key i * 32 + l: tile order), so the
+// ranks are stable.  One pass over the [warp][digit] counters (512 threads, 24
+// shared-memory accesses each) turns them into the first slot of every (warp, digit)
+// pair in the sorted tile; the sorted tile leaves in 16 slices of 512 slots, one per
+// warp, the digit of every slot (one byte, written beside the element) selecting the
+// run's shift to its global position (coalesced stores within a run; balanced
+// whatever the digit distribution).
+// Used for 65 .. 256 buckets (one pass); see rw_wanted() for why not beyond.
+static constexpr int RW_THREADS = 512, RW_WARPS = RW_THREADS / 32, RW_ITEMS = 16;
+static constexpr uint32_t RW_NB = 256, RW_TILE = RW_THREADS * RW_ITEMS, RW_WARP_KEYS = 32 * RW_ITEMS;
+static_assert(RW_TILE == 8192, "the tile geometry of the count table");
+
+template <int OUT> constexpr size_t rw_smem_bytes() {
+    // match words + counters [warp][digit], sorted tile (two arrays for pairs), run shifts, slot digits
+    return (size_t) (2 * RW_WARPS * RW_NB + (OUT == RK_OUT_PAIRS ? 2 : 1) * RW_TILE + RW_NB) * 4 + RW_TILE;
+}
+
+template <int IN, int OUT>
+__global__ void __launch_bounds__(RW_THREADS, 2)
+mkperm_rank_wide_kernel(const RkArgs a) {
+    constexpr uint32_t NB = RW_NB, ITEMS = RW_ITEMS, HALFW = RW_WARPS / 2;
+    static_assert(IN == RK_RAW || IN == RK_PAIRS ? OUT != RK_FINAL || IN == RK_PAIRS : OUT != RK_OUT_PAIRS,
+                  "unsupported combination");
+    extern __shared__ __align__(16) uint32_t rw_smem[];
+    uint32_t *s_mask = rw_smem;                                              // [warp][digit]
+    uint32_t *s_cnt = s_mask + RW_WARPS * NB;                                // [warp][digit]
+    uint32_t *s_stage = s_cnt + RW_WARPS * NB;                               // sorted tile
+    uint32_t *s_stage1 = s_stage + RW_TILE;                                  // (pairs: the indices)
+    uint32_t *s_gdelta = s_stage + (OUT == RK_OUT_PAIRS ? 2 : 1) * RW_TILE;  // global slot - sorted-tile slot
+    uint8_t *s_dig = (uint8_t *) (s_gdelta + NB);                            // digit of every sorted slot
+    __shared__ uint32_t s_wsum[RW_WARPS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bit = 1u << lane, lt = bit - 1u;
+    uint32_t *my_mask = s_mask + warp * NB, *my_cnt = s_cnt + warp * NB;
+    // the match words start out zero and every step leaves them zero again
+    #pragma unroll
+    for (uint32_t i = lane; i < NB; i += 32) {
+        my_mask[i] = 0;
+        my_cnt[i] = 0;
+    }
+    __syncwarp();
+    const uint32_t idxmask = a.ib >= 32 ? 0xffffffffu : (1u << a.ib) - 1u;
+    auto digit = [&](uint32_t x) -> uint32_t {
+        if constexpr (IN == RK_RAW1)
+            return x;
+        else
+            return (x >> a.shift) & a.mask;
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < a.geom.ntiles; tile += gridDim.x) {
+        uint32_t base, count;
+        tile_range<RW_TILE>(a.geom, tile, base, count);
+        if (count == 0) // block-uniform
+            continue;
+        const bool full = count == RW_TILE;
+        const uint32_t first = warp * RW_WARP_KEYS + lane; // tile-local index of this lane's key of step 0
+
+        // ---- load: step i of a warp = 32 consecutive keys
+        uint32_t key[ITEMS], idx[IN == RK_PAIRS ? ITEMS : 1];
+        #pragma unroll
+        for (int i = 0; i < (int) ITEMS; ++i) {
+            const uint32_t li = first + i * 32;
+            key[i] = full || li < count ? __ldg(a.in0 + base + li) : 0u;
+            if constexpr (IN == RK_PAIRS)
+                idx[i] = full || li < count ? __ldg(a.in1 + base + li) : 0u;
+        }
+        // first output slot of this tile's run of digit tid
+        uint32_t gstart = 0;
+        if (tid < a.bins) {
+            const uint32_t group_start = a.geom.tpg == a.geom.ntiles ? 0u : (tile / a.geom.tpg) * a.geom.group_size;
+            gstart = group_start + __ldg(a.table + (table_index(a.geom, tile, tid, a.bins) >> 1));
+        }
+        if constexpr (IN == RK_RAW1 || IN == RK_RAW) {
+            #pragma unroll
+            for (int i = 0; i < (int) ITEMS; ++i)
+                key[i] = min(key[i], a.kmax);
+        }
+
+        // ---- rank inside the warp
+        uint32_t rk[ITEMS / 2];
+        #pragma unroll
+        for (int i = 0; i < (int) ITEMS; ++i) {
+            const bool valid = full || first + i * 32 < count;
+            const uint32_t d = digit(key[i]);
+            if (valid)
+                atomicOr(my_mask + d, bit);
+            __syncwarp();
+            const uint32_t m = my_mask[d], c = my_cnt[d];
+            const uint32_t r = __popc(m & lt);
+            __syncwarp();
+            if (valid && r == 0) {
+                my_mask[d] = 0;
+                my_cnt[d] = c + __popc(m);
+            }
+            __syncwarp();
+            if (i & 1)
+                rk[i / 2] |= (c + r) << 16;
+            else
+                rk[i / 2] = c + r;
+        }
+        __syncthreads(); // (the previous tile's slices have left, too)
+
+        // ---- counters -> first sorted-tile slot of every (warp, digit) pair.  Thread
+        // (dg, sub) owns digit dg of the warps [8 sub, 8 sub + 8).
+        {
+            const uint32_t dg = tid & (NB - 1), sub = tid / NB;
+            static_assert(RW_THREADS == 2 * NB, "two threads per digit");
+            uint32_t c8[HALFW], own = 0, other = 0;
+            #pragma unroll
+            for (uint32_t j = 0; j < HALFW; ++j) {
+                c8[j] = s_cnt[(sub * HALFW + j) * NB + dg];
+                own += c8[j];
+            }
+            #pragma unroll
+            for (uint32_t j = 0; j < HALFW; ++j)
+                other += s_cnt[((sub ^ 1u) * HALFW + j) * NB + dg];
+            const uint32_t total = own + other;
+            uint32_t incl = total; // scan over the digits (both halves of the CTA, redundantly)
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL_MASK, incl, d);
+                if (lane >= (uint32_t) d)
+                    incl += up;
+            }
+            if (lane == 31)
+                s_wsum[warp] = incl;
+            __syncthreads();
+            const uint32_t wt = lane < (warp & (HALFW - 1)) ? s_wsum[sub * HALFW + lane] : 0u;
+            const uint32_t dstart = __reduce_add_sync(FULL_MASK, wt) + incl - total;
+            uint32_t running = dstart + (sub ? other : 0u);
+            #pragma unroll
+            for (uint32_t j = 0; j < HALFW; ++j) {
+                s_cnt[(sub * HALFW + j) * NB + dg] = running;
+                running += c8[j];
+            }
+            if (sub == 0)
+                s_gdelta[dg] = gstart - dstart;
+        }
+        __syncthreads();
+
+        // ---- place
+        #pragma unroll
+        for (int i = 0; i < (int) ITEMS; ++i) {
+            const uint32_t li = first + i * 32;
+            if (full || li < count) {
+                const uint32_t w = key[i], d = digit(w);
+                const uint32_t slot = my_cnt[d] + ((rk[i / 2] >> (16 * (i & 1))) & 0xffffu);
+                s_dig[slot] = (uint8_t) d;
+                uint32_t v;
+                if constexpr (IN == RK_RAW1) {
+                    v = a.index_base + base + li;
+                } else if constexpr (IN == RK_PACKED) {
+                    v = OUT == RK_FINAL ? w & idxmask : ((w >> (a.ib + a.width)) << a.ib) | (w & idxmask);
+                } else {
+                    const uint32_t ix = IN == RK_PAIRS ? idx[i] : a.index_base + base + li;
+                    if constexpr (OUT == RK_FINAL)
+                        v = ix;
+                    else if constexpr (OUT == RK_OUT_PACKED)
+                        v = ((w >> (a.shift + a.width)) << a.ib) | ix;
+                    else {
+                        v = w;
+                        s_stage1[slot] = ix;
+                    }
+                }
+                s_stage[slot] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- the warp's counters are its own again
+        #pragma unroll
+        for (uint32_t i = lane; i < NB; i += 32)
+            my_cnt[i] = 0;
+
+        // ---- write: warp w moves the sorted slots [512 w, 512 w + 512): consecutive
+        // lanes hold consecutive slots, i.e. (mostly) consecutive addresses of one run
+        #pragma unroll 4
+        for (int i = 0; i < (int) ITEMS; ++i) {
+            const uint32_t k = first + i * 32;
+            if (full || k < count) {
+                const uint32_t to = s_gdelta[s_dig[k]] + k;
+                a.out0[to] = s_stage[k];
+                if constexpr (OUT == RK_OUT_PAIRS)
+                    a.out1[to] = s_stage1[k];
+            }
+        }
+    }
+}
+
+template <int IN, int OUT>
+static cudaError_t rw_launch_cfg(cudaStream_t stream, const RkArgs &a) {
+    constexpr size_t smem = rw_smem_bytes<OUT>();
+    auto kernel = mkperm_rank_wide_kernel<IN, OUT>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess)
+        return err;
+    const uint32_t grid = std::min<uint32_t>(a.geom.ntiles, 2u * (uint32_t) sm_count());
+    kernel<<<grid, RW_THREADS, smem, stream>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static cudaError_t rw_launch(cudaStream_t stream, int in, int out, const RkArgs &a) {
+    switch (in * 4 + out) {
+        case RK_RAW1 * 4 + RK_FINAL: return rw_launch_cfg<RK_RAW1, RK_FINAL>(stream, a);
+        case RK_RAW * 4 + RK_OUT_PAIRS: return rw_launch_cfg<RK_RAW, RK_OUT_PAIRS>(stream, a);
+        case RK_RAW * 4 + RK_OUT_PACKED: return rw_launch_cfg<RK_RAW, RK_OUT_PACKED>(stream, a);
+        case RK_PAIRS * 4 + RK_FINAL: return rw_launch_cfg<RK_PAIRS, RK_FINAL>(stream, a);
+        case RK_PAIRS * 4 + RK_OUT_PAIRS: return rw_launch_cfg<RK_PAIRS, RK_OUT_PAIRS>(stream, a);
+        case RK_PAIRS * 4 + RK_OUT_PACKED: return rw_launch_cfg<RK_PAIRS, RK_OUT_PACKED>(stream, a);
+        case RK_PACKED * 4 + RK_FINAL: return rw_launch_cfg<RK_PACKED, RK_FINAL>(stream, a);
+        case RK_PACKED * 4 + RK_OUT_PACKED: return rw_launch_cfg<RK_PACKED, RK_OUT_PACKED>(stream, a);
+    }
+    return cudaErrorInvalidValue;
+}
+
+/// Digits wider than six bits for this many key bits?  (B200_MKPERM_WIDE: 0 never, 2
+/// whenever the key has more than six bits; development switch)
+static bool rw_wanted(uint32_t total_bits) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("B200_MKPERM_WIDE");
+        mode = e ? atoi(e) : 1;
+    }
+    if (mode == 0 || total_bits <= 6 || rk_tile_keys() != RW_TILE)
+        return false;
+    if (mode == 2)
+        return true;
+    // 7-8 bits: one wide pass (0.44 ms for 2^26 keys) instead of two 4-bit ones (0.48 ms).
+    // Beyond that the wide passes lose: a 16-bit key takes 1.11 ms in two 8-bit passes
+    // against 0.94 ms in three of 5 / 5 / 6 bits -- per key and pass the warp-private
+    // tables cost 33 shared-memory wavefronts per 32 keys (every access hits a random
+    // bank: 3.4-way conflicts on average), the thread-private columns 9 to 11.
+    return total_bits <= 8;
+}
+
 template <uint32_t TILE>
 static void tile_hist_launch(cudaStream_t stream, int form, const uint32_t *in0, const RkArgs &a) {
     const uint32_t grid = (uint32_t) ceil_div(a.geom.ntiles, MT_GROUP / 2);
@@ -995,15 +1250,15 @@ static void tile_hist_launch(cudaStream_t stream, int form, const uint32_t *in0,
     switch (form) {
         case RK_RAW1:
             mkperm_tile_hist_kernel<RK_RAW1, TILE><<<grid, MT_THREADS, smem, stream>>>(
-                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, table);
+                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, a.halves, table);
             break;
         case RK_RAW:
             mkperm_tile_hist_kernel<RK_RAW, TILE><<<grid, MT_THREADS, smem, stream>>>(
-                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, table);
+                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, a.halves, table);
             break;
         default:
             mkperm_tile_hist_kernel<RK_PACKED, TILE><<<grid, MT_THREADS, smem, stream>>>(
-                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, table);
+                in0, a.geom, a.shift, a.mask, a.kmax, a.bins, a.halves, table);
     }
     count_launch();
 }
@@ -1059,7 +1314,9 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
     uint32_t ib = 1;
     while (ib < 32 && (1ull << ib) < (uint64_t) index_base + size)
         ib++;
-    const uint32_t npasses = (total_bits + 5) / 6;
+    const bool wide = rw_wanted(total_bits);
+    const uint32_t npasses = wide ? (total_bits + 7) / 8 : (total_bits + 5) / 6;
+    const uint32_t halves = wide ? 1 : 2;
     TileGeom geom{};
     geom.size = size;
     geom.group_size = group_size;
@@ -1080,7 +1337,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
         sh += width[p];
     }
 
-    const uint64_t max_counts = (uint64_t) 64 * 2 * ntiles;
+    const uint64_t max_counts = (uint64_t) (wide ? 256 : 128) * ntiles;
     uint32_t *table = (uint32_t *) temp_alloc(max_counts * 4, stream);
     uint32_t *tmp[4] = { nullptr, nullptr, nullptr, nullptr };
     auto cleanup = [&]() {
@@ -1105,6 +1362,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
         a.kmax = bucket_count - 1;
         a.width = width[p];
         a.index_base = index_base;
+        a.halves = halves;
         if (form == RK_RAW1) {
             a.shift = 0;
             a.mask = 0xffffffffu;
@@ -1136,14 +1394,14 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
             a.out1 = tmp[set + 1];
         }
 
-        const uint64_t ncounts = (uint64_t) a.bins * 2 * ntiles;
+        const uint64_t ncounts = (uint64_t) a.bins * halves * ntiles;
         if (tile_keys == 4096)
             tile_hist_launch<4096>(stream, form, in0, a);
         else
             tile_hist_launch<8192>(stream, form, in0, a);
         // one exclusive scan per group over its [digit][tile][half] counts
         int rc = b200_block_prefix_reduce(stream, B200_VT_UINT32, B200_OP_ADD, ncounts,
-                                          (uint64_t) a.bins * geom.tpg * 2, 1, 0, table, table);
+                                          (uint64_t) a.bins * geom.tpg * halves, 1, 0, table, table);
         if (rc) {
             cleanup();
             return rc;
@@ -1155,7 +1413,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
                 cleanup();
                 return fail(B200_ERR_CUDA, "jit_block_mkperm(): out of memory");
             }
-            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(table, 2 * (uint64_t) ntiles, bucket_count, size, records);
+            mkperm_offsets_kernel<<<1, 1024, 0, stream>>>(table, halves * (uint64_t) ntiles, bucket_count, size, records);
             count_launch();
             rc = deliver_records(stream, records, bucket_count, offsets, by_size);
             temp_free(records, stream);
@@ -1165,7 +1423,7 @@ static int mkperm_ranked(cudaStream_t stream, const uint32_t *values, uint32_t s
             }
         }
         const uint32_t bits = form == RK_RAW1 ? std::max(3u, total_bits) : std::max(3u, width[p]);
-        cudaError_t err = rk_launch(stream, (int) bits, form, out, a);
+        cudaError_t err = wide ? rw_launch(stream, form, out, a) : rk_launch(stream, (int) bits, form, out, a);
         if (err != cudaSuccess) {
             cleanup();
             return cuda_fail(err, "mkperm_rank_place_kernel");

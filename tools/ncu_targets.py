@@ -44,6 +44,10 @@ def main():
             k = torch.randint(0, B, (n2,), device="cuda", dtype=torch.int32)
             offs = torch.zeros(4 * B + 1, dtype=torch.int32).pin_memory()
             dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, offs)
+    if "mkperm256" in want:
+        perm = torch.empty(n2, device="cuda", dtype=torch.int32)
+        k = torch.randint(0, 256, (n2,), device="cuda", dtype=torch.int32)
+        dr.jit_block_mkperm(CUDA, k, n2, n2, 256, perm, None)
     if "scatter" in want:
         m2 = 1 << 20
         idx = torch.randint(0, m2, (n2,), device="cuda", dtype=torch.int32)

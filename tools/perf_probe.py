@@ -87,7 +87,7 @@ def main():
 
     n2 = 1 << 26
     perm = torch.empty(n2, device="cuda", dtype=torch.int32)
-    for B in (16, 1024, 65536) if on("mkperm") else []:
+    for B in (16, 256, 1024, 65536) if on("mkperm") else []:
         k = torch.randint(0, B, (n2,), device="cuda", dtype=torch.int32)
         offs = torch.zeros(4 * B + 1, dtype=torch.int32).pin_memory()
         ms = timeit(lambda: dr.jit_block_mkperm(CUDA, k, n2, n2, B, perm, offs), iters=5)
