@@ -122,6 +122,7 @@ def lib():
         L.b200_sharded_connect.argtypes = [vp, vp]
         L.b200_sharded_destroy.argtypes = [vp]
         L.b200_sharded_reduce.argtypes = [vp, vp, i, i, vp, u64, vp]
+        L.b200_sharded_reduce_dot.argtypes = [vp, vp, i, vp, vp, u64, vp]
         L.b200_sharded_prefix_reduce.argtypes = [vp, vp, i, i, u64, i, i, vp, vp]
         L.b200_sharded_prefix_reduce_cyclic.argtypes = [vp, vp, i, i, u64, u64, i, vp, vp]
         L.b200_sharded_histogram.argtypes = [vp, vp, vp, u64, u32, vp, vp]
@@ -478,6 +479,10 @@ class ShardedContext:
     def reduce(self, vt, op, in_, local_size, out, stream=None):
         _check(lib().b200_sharded_reduce(self._ctx, _stream(stream), vt, op, _ptr(in_), local_size,
                                          _ptr(out)))
+
+    def reduce_dot(self, vt, a, b, local_size, out, stream=None):
+        _check(lib().b200_sharded_reduce_dot(self._ctx, _stream(stream), vt, _ptr(a), _ptr(b), local_size,
+                                             _ptr(out)))
 
     def prefix_reduce(self, vt, op, local_size, exclusive, reverse, in_, out, stream=None):
         _check(lib().b200_sharded_prefix_reduce(self._ctx, _stream(stream), vt, op, local_size,

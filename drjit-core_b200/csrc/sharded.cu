@@ -519,6 +519,27 @@ int b200_sharded_reduce(B200Sharded *c, void *stream_, int vt, int op, const voi
     return fn(c, stream, peer_table(c), partial, out);
 }
 
+int b200_sharded_reduce_dot(B200Sharded *c, void *stream_, int vt, const void *a, const void *b,
+                            uint64_t local_size, void *out) {
+    int rc = check_ctx(c, "b200_sharded_reduce_dot()");
+    if (rc)
+        return rc;
+    ShardReduceFn fn = vt == B200_VT_FLOAT16 || vt == B200_VT_FLOAT32 || vt == B200_VT_FLOAT64
+                           ? reduce_exchange_for(vt, B200_OP_ADD) : nullptr;
+    if (!fn)
+        return fail(B200_ERR_UNSUPPORTED, "b200_sharded_reduce_dot(): no existing kernel for type=%s!", type_name(vt));
+    cudaStream_t stream = resolve_stream(stream_);
+    void *partial = c->scalars;
+    if (local_size > 0) {
+        if ((rc = b200_reduce_dot(stream, vt, a, b, local_size, partial)))
+            return rc;
+    } else {
+        B200_CUDA_CHECK(cudaMemsetAsync(partial, 0, 8, stream));
+    }
+    c->epoch++;
+    return fn(c, stream, peer_table(c), partial, out);
+}
+
 int b200_sharded_prefix_reduce(B200Sharded *c, void *stream_, int vt, int op, uint64_t local_size,
                                int exclusive, int reverse, const void *in, void *out) {
     int rc = check_ctx(c, "b200_sharded_prefix_reduce()");

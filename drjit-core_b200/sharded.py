@@ -12,6 +12,7 @@ Exchange steps (payloads are a few bytes to a few KiB, i.e. latency bound):
   reduce     local reduce -> all_gather of the W partials -> every rank
              combines them in rank order (bit-exact for integers, and the same
              fixed order on every rank for floating point).
+  dot        the same with a local dot product in front (rank-order sum).
   scan       local reduce -> all_gather of the W totals -> exclusive scan of
              the totals (tiny, on device) -> local scan seeded with the rank's
              carry.  12 B/element per GPU instead of 8, so the ceiling against a
@@ -32,7 +33,7 @@ import torch
 import torch.distributed as dist
 
 from . import (JitBackend, ReduceOp, TYPE_SIZE, VarType, jit_block_prefix_reduce,
-               jit_block_reduce, jit_reduce, mkperm_histogram, prefix_reduce_carry,
+               jit_block_reduce, jit_reduce, jit_reduce_dot, mkperm_histogram, prefix_reduce_carry,
                prefix_reduce_seeded, scan_tile_elems)
 
 
@@ -46,6 +47,9 @@ class CudaLocalOps:
 
     def reduce(self, vt, op, in_, size, out):
         jit_reduce(JitBackend.CUDA, vt, op, in_, size, out)
+
+    def reduce_dot(self, vt, a, b, size, out):
+        jit_reduce_dot(JitBackend.CUDA, vt, a, b, size, out)
 
     def block_reduce(self, vt, op, size, block_size, in_, out):
         jit_block_reduce(JitBackend.CUDA, vt, op, size, block_size, in_, out)
@@ -161,6 +165,20 @@ class Sharded:
             self._fill_identity(partial, vt, op)
         gathered = self._gather(partial)
         self.ops.block_reduce(vt, op, self.world, self.world, gathered, out)
+
+    def reduce_dot(self, vt, local_a, local_b, local_size, out):
+        """Dot product of two equally sharded float arrays; every rank receives the
+        result in `out` (device scalar of type vt; rank-order sum of the partials)."""
+        if self.peer is not None:
+            self.peer.reduce_dot(vt, local_a, local_b, local_size, out)
+            return
+        partial = self._bytes(TYPE_SIZE[vt])
+        if local_size > 0:
+            self.ops.reduce_dot(vt, local_a, local_b, local_size, partial)
+        else:
+            partial.zero_()
+        gathered = self._gather(partial)
+        self.ops.block_reduce(vt, ReduceOp.Add, self.world, self.world, gathered, out)
 
     def _fill_identity(self, buf, vt, op):
         from . import jit_reduce_identity

@@ -352,6 +352,12 @@ B200_API int b200_sharded_destroy(B200Sharded *ctx);
 B200_API int b200_sharded_reduce(B200Sharded *ctx, void *stream, int vt, int op, const void *in,
                                  uint64_t local_size, void *out);
 
+/* Dot product of two equally sharded arrays ("reduce / block_reduce / dot"):
+ * jitc_reduce_dot (src/util.cpp:63-67) on the shard, then the exchange of
+ * b200_sharded_reduce with ReduceOp::Add; every rank receives the result.  f16 / f32 / f64. */
+B200_API int b200_sharded_reduce_dot(B200Sharded *ctx, void *stream, int vt, const void *a, const void *b,
+                                     uint64_t local_size, void *out);
+
 /* Prefix reduction of the global array (block_size == global size); rank r's shard
  * of the result goes to `out`.  16-byte aligned shards of fewer than 2^32 - 2^14
  * elements; no float16.  Three launches per rank: tile sums of the shard, one CTA

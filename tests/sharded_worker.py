@@ -62,6 +62,17 @@ def main():
                         ref = O.block_reduce(vt, op, x, total)[0]
                         if got != ref:
                             bad.append((exchange, "reduce", tname, opn, total, int(got), int(ref)))
+                    # ---- dot product of two equally sharded arrays (float types)
+                    if tname == "f32" and opn == "add":
+                        y = x[::-1].copy()
+                        d_y = to_dev(y[start:start + n_local])
+                        d_o = torch.zeros(4, dtype=torch.int64, device=dev)
+                        sh.reduce_dot(vt, d_x, d_y, n_local, d_o)
+                        torch.cuda.synchronize()
+                        got = float(d_o.cpu().numpy().view(dt)[0])
+                        ref = float(np.dot(x.astype(np.float64), y.astype(np.float64)))
+                        if abs(got - ref) > 1e-5 * abs(ref):
+                            bad.append((exchange, "dot", tname, total, got, ref))
                     # ---- whole-array prefix reduction: fwd / rev x exclusive / inclusive
                     for excl in (1, 0):
                         for rev in (0, 1):

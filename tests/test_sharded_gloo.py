@@ -34,6 +34,9 @@ class OracleLocalOps:
         r = self.O.block_reduce(vt, op, self._view(in_, vt, size), block_size)
         self._view(out, vt, r.size)[:] = r
 
+    def reduce_dot(self, vt, a, b, size, out):
+        self._view(out, vt, 1)[:] = self.O.reduce_dot(vt, self._view(a, vt, size), self._view(b, vt, size))
+
     def block_prefix_reduce(self, vt, op, size, block_size, exclusive, reverse, in_, out):
         r = self.O.block_prefix_reduce(vt, op, self._view(in_, vt, size), block_size, exclusive, reverse)
         self._view(out, vt, size)[:] = r
@@ -122,6 +125,16 @@ def _worker(rank, world, port, results):
         gathered = [None] * world
         dist.all_gather_object(gathered, float(got))
         ok &= len(set(gathered)) == 1
+        # dot product of two equally sharded arrays (an empty shard contributes zero)
+        for total in (1, 50001):
+            xa, xb = f32_input(total), f32_input(total)[::-1].copy()
+            start, n = shard_bounds(total, world, rank)
+            out = torch.zeros(4, dtype=torch.uint8)
+            sh.reduce_dot(VT["f32"], torch.from_numpy(xa[start:start + n].copy().view(np.uint8)),
+                          torch.from_numpy(xb[start:start + n].copy().view(np.uint8)), n, out)
+            got = out.numpy().view(np.float32)[0]
+            ref = float(np.dot(xa.astype(np.float64), xb.astype(np.float64)))
+            ok &= abs(got - ref) <= 1e-5 * abs(ref)
         results[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
