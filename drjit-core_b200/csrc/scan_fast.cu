@@ -11,12 +11,18 @@
 //   CHAIN  the whole array is one block (optionally seeded with a carry), or
 //          block_size is a power-of-two multiple of the tile: tiles are chained
 //          with decoupled look-back over 64-bit {status, value} descriptors.
-//   In both modes tiles are handed out by an atomic ticket: every predecessor
+//   SEG    any other block size: CHAIN with block boundaries at arbitrary elements.
+//          Boundaries are regular, so no head flags travel through the scan: every
+//          combine step is guarded by the distance of a vector to the most recent
+//          block start, which each thread derives arithmetically.  A tile that
+//          contains a block start publishes the aggregate of its tail as an inclusive
+//          prefix at once, which is also what stops the look-back at block borders.
+//   In all modes tiles are handed out by an atomic ticket: every predecessor
 //   of a tile is therefore owned by a CTA that is already running (forward
 //   progress of the look-back), and fast SMs take more tiles (load balance).
 //
-// Everything else (odd block sizes, pointers that are not 16-byte aligned) is
-// served by the general segmented kernel in scan.cu.
+// Pointers that are not 16-byte aligned (and the carry / seeded entry points with
+// such pointers) are served by the general segmented kernel in scan.cu.
 //
 // Kernel structure (persistent CTAs, 512 compute threads):
 //   - a tile is 512 * J 16-byte vectors (32 KiB for J = 4).  Thread 0 keeps a
@@ -59,6 +65,8 @@ struct FastParams {
     uint32_t log2_bs;    // POW2: log2(block_size)
     uint32_t seg_mask;   // CHAIN: tiles per block - 1 (0xffffffff: one block)
     uint32_t tile_off;   // CHAIN: phase of the block grid in logical tile space
+    uint32_t bs;         // SEG: block size; logical element I starts a block iff (I + off) % bs == 0
+    uint32_t off;        // SEG: phase of the block grid in logical element space
     uint32_t exclusive;
     uint32_t reverse;
     uint32_t debug;      // development switches
@@ -225,12 +233,95 @@ template <typename T, int Op, int J, int THREADS, bool FULL> struct TileScan {
     }
 };
 
+/// Position inside its block of the element `delta` (< bs) elements after one at position `pos` (< bs)
+B200_DEVICE uint32_t seg_advance(uint32_t pos, uint32_t delta, uint32_t bs) {
+    return delta >= bs - pos ? delta - (bs - pos) : pos + delta;
+}
+
+/// TileScan for blocks of ANY size `bs` >= 2 (SEG).  sv[j]: position of the vector's first
+/// element inside its block (0: it starts a block).  On exit e[j][k] is the inclusive prefix
+/// since the nearest block start INSIDE the vector (or since the vector's start), carry[j] the
+/// reduction of the elements of this tile in front of the vector that belong to the block of
+/// its first element.  It applies to the elements in front of the vector's first block start.
+template <typename T, int Op, int J, int THREADS> struct TileScanSeg {
+    using V = typename ValueOf<T>::type;
+    using R = Red<V, Op>;
+    static constexpr int N = VecInfo<T>::N;
+    static constexpr int WARPS = THREADS / 32;
+
+    static B200_DEVICE void run(V (&e)[J][N], V (&carry)[J], const uint32_t (&sv)[J], uint32_t bs, uint32_t lane,
+                                uint32_t warp, V *s_warp, uint32_t *s_wt) {
+        // ---- inside the vector; t[j]: elements from the last block start through the vector's end
+        uint32_t t[J];
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            uint32_t pos = sv[j];
+            #pragma unroll
+            for (int k = 1; k < N; ++k) {
+                pos = pos + 1 == bs ? 0u : pos + 1;
+                if (pos != 0)
+                    e[j][k] = R::apply(e[j][k - 1], e[j][k]);
+            }
+            t[j] = pos + 1;
+        }
+        // ---- inside a row: the vector d lanes down belongs to my block iff t > d * N
+        V a[J];
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            a[j] = e[j][N - 1];
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            #pragma unroll
+            for (int j = 0; j < J; ++j) {
+                V up = shfl_up(a[j], d);
+                if (lane >= (uint32_t) d && t[j] > (uint32_t) (d * N))
+                    a[j] = R::apply(up, a[j]);
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            V up = shfl_up(a[j], 1);
+            carry[j] = lane && sv[j] ? up : R::identity();
+        }
+        // ---- across the rows of a warp: `run` = the tail of the rows so far
+        V run = R::identity();
+        uint32_t tr = 0;
+        #pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const V rt = shfl_idx(a[j], 31);
+            tr = __shfl_sync(FULL_MASK, t[j], 31);
+            if (sv[j] > lane * N) // the vector's block starts in front of this row
+                carry[j] = R::apply(run, carry[j]);
+            run = tr > 32u * N ? R::apply(run, rt) : rt;
+        }
+        // ---- across warps
+        if (lane == 0) {
+            s_warp[warp] = run;
+            s_wt[warp] = tr;
+        }
+        compute_sync<THREADS>();
+        V wc = R::identity();
+        #pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const V wv = s_warp[w];
+            const uint32_t wt = s_wt[w];
+            if ((uint32_t) w < warp)
+                wc = wt > (uint32_t) (J * 32 * N) ? R::apply(wc, wv) : wv;
+        }
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (sv[j] > (j * 32 + lane) * N) // ... in front of this warp's rows
+                carry[j] = R::apply(wc, carry[j]);
+    }
+};
+
 /// THREADS compute threads (+ one look-back warp when CHAIN), tiles of
 /// THREADS * J vectors, ring of S shared-memory slots.
-template <typename T, int Op, int J, int S, int THREADS, bool CHAIN, int LB, int LBW>
+template <typename T, int Op, int J, int S, int THREADS, bool CHAIN, int LB, int LBW, bool SEG = false>
 __global__ void __launch_bounds__(THREADS + (CHAIN ? 32 + 32 * LB : 0),
                                   (THREADS >= 512 && (size_t) S * THREADS * J * 16 <= 112 * 1024) ? 2 : 1)
 scan_stream_kernel(const FastParams p) {
+    static_assert(CHAIN || !SEG, "SEG is a CHAIN mode");
     using V = typename ValueOf<T>::type;
     using R = Red<V, Op>;
     constexpr int N = VecInfo<T>::N;
@@ -252,7 +343,10 @@ scan_stream_kernel(const FastParams p) {
     __shared__ __align__(8) uint64_t s_agg[M];   // s_total / s_mtile entry is valid
     __shared__ __align__(8) uint64_t s_pref[M];  // s_prefix entry is valid
     __shared__ uint32_t s_tile[S];
+    __shared__ uint32_t s_spos[S];   // SEG: position of the tile's first logical element inside its block
     __shared__ uint32_t s_mtile[M];
+    __shared__ uint32_t s_mseg[M];   // SEG: bit 0 = the tile contains a block start, bit 1 = it begins with one
+    __shared__ uint32_t s_wt[WARPS];
     __shared__ V s_total[M];
     __shared__ V s_prefix[M];
     __shared__ V s_warp[WARPS];
@@ -274,6 +368,8 @@ scan_stream_kernel(const FastParams p) {
             return;
         }
         s_tile[slot] = t;
+        if constexpr (SEG)
+            s_spos[slot] = (uint32_t) (((uint64_t) t * TILE + p.off) % p.bs);
         const uint32_t pt = p.reverse ? p.ntiles - 1 - t : t;
         const uint64_t base = (uint64_t) pt * TILE;
         if (base + TILE <= p.size) {
@@ -400,9 +496,26 @@ scan_stream_kernel(const FastParams p) {
                 #pragma unroll
                 for (int u = 0; u < AU; ++u)
                     acc[u] = R::identity();
+                // SEG: only the tile's tail -- the elements from its last block start on --
+                // reaches the tiles behind it: PHYSICAL elements [lo, hi) of the tile
+                uint32_t lo = 0, hi = TILE, seg_bits = 0;
+                if constexpr (SEG) {
+                    const uint32_t spos = s_spos[slot];
+                    const uint32_t t_end = seg_advance(spos, (TILE - 1) % p.bs, p.bs) + 1;
+                    const bool has_head = p.bs <= TILE || t_end <= TILE;
+                    seg_bits = (has_head ? 1u : 0u) | (spos == 0 ? 2u : 0u);
+                    if (has_head) {
+                        if (p.reverse)
+                            hi = t_end;
+                        else
+                            lo = TILE - t_end;
+                    }
+                }
                 if (base + TILE <= p.size) {
                     #pragma unroll 1
-                    for (uint32_t i = lane; i < VECS; i += 32 * AU) {
+                    for (uint32_t i = SEG ? (lo / N / (32 * AU)) * (32 * AU) + lane : lane; i < VECS; i += 32 * AU) {
+                        if (SEG && i - lane >= hi / N + 1)
+                            break; // (warp-uniform)
                         Vec16<T> v[AU];
                         #pragma unroll
                         for (int u = 0; u < AU; ++u)
@@ -414,6 +527,15 @@ scan_stream_kernel(const FastParams p) {
                             #pragma unroll
                             for (int kk = 0; kk < N; ++kk)
                                 t[kk] = to_value<T>(v[u].elem[kk]);
+                            if constexpr (SEG) {
+                                const uint32_t pe = (i + u * 32) * N;
+                                if (pe < lo || pe + N > hi) {
+                                    #pragma unroll
+                                    for (int kk = 0; kk < N; ++kk)
+                                        if (pe + kk < lo || pe + kk >= hi)
+                                            t[kk] = R::identity();
+                                }
+                            }
                             #pragma unroll
                             for (int w = N / 2; w > 0; w >>= 1) {
                                 #pragma unroll
@@ -424,7 +546,7 @@ scan_stream_kernel(const FastParams p) {
                         }
                     }
                 } else {
-                    for (uint64_t i = base + lane; i < p.size; i += 32)
+                    for (uint64_t i = base + lo + lane; i < p.size && i < base + hi; i += 32)
                         acc[0] = R::apply(acc[0], to_value<T>(in[i]));
                 }
                 #pragma unroll
@@ -435,7 +557,10 @@ scan_stream_kernel(const FastParams p) {
                 }
                 const V total = warp_reduce<V, Op>(acc[0]);
                 if (lane == 0) {
-                    const bool first = ((tile + p.tile_off) & p.seg_mask) == 0;
+                    // (SEG: a tile with a block start inside publishes its tail as a prefix)
+                    const bool first = SEG ? tile == 0 || (seg_bits & 1u) : ((tile + p.tile_off) & p.seg_mask) == 0;
+                    if constexpr (SEG)
+                        s_mseg[m] = seg_bits;
                     if (first) {
                         V P = R::identity();
                         if (p.carry_in)
@@ -487,7 +612,9 @@ scan_stream_kernel(const FastParams p) {
                 DBG_ADD(7, c1 - c0);
                 DBG_ADD(5, 1);
                 const V total = s_total[m];
-                const bool first = ((tile + p.tile_off) & p.seg_mask) == 0;
+                // SEG: no prefix to find when the tile begins with a block start; nothing to
+                // publish when it contains one (the aggregate warp has done that already)
+                const bool first = SEG ? tile == 0 || (s_mseg[m] & 2u) : ((tile + p.tile_off) & p.seg_mask) == 0;
                 V P = R::identity();
                 if (p.seeds) {
                     // SEEDED: the caller knows every tile's exclusive prefix (tile sums
@@ -498,7 +625,7 @@ scan_stream_kernel(const FastParams p) {
                         P = *(const V *) p.carry_in;
                 } else {
                     P = look_back(tile);
-                    if (lane == 0)
+                    if (lane == 0 && !(SEG && (s_mseg[m] & 1u)))
                         Desc<V>::publish(p.desc, tile, DESC_PREFIX, R::apply(P, total));
                 }
                 if (p.cyc.world) {
@@ -584,6 +711,13 @@ scan_stream_kernel(const FastParams p) {
     }
 
     // ---- compute warps
+    // SEG: position inside a block of this thread's vectors when the tile starts a block
+    uint32_t seg_r[SEG ? J : 1] = {};
+    if constexpr (SEG) {
+        #pragma unroll
+        for (int j = 0; j < J; ++j)
+            seg_r[j] = ((warp * (J * 32) + j * 32 + lane) * N) % p.bs;
+    }
     long long loop0 = DBG_CLOCK();
     for (uint32_t k = 0;; ++k) {
         const uint32_t slot = k % S;
@@ -604,6 +738,13 @@ scan_stream_kernel(const FastParams p) {
         const uint64_t base = (uint64_t) ptile * TILE;
         const bool bulk = base + TILE <= p.size; // CTA-uniform
         const uint4 *slot_ptr = slots + (size_t) slot * VECS;
+        uint32_t sv[SEG ? J : 1] = {};
+        if constexpr (SEG) {
+            const uint32_t spos = s_spos[slot];
+            #pragma unroll
+            for (int j = 0; j < J; ++j)
+                sv[j] = seg_advance(spos, seg_r[j], p.bs);
+        }
 
         // ---- load (logical vector lvi of the tile <-> physical vector pvi)
         V e[J][N];
@@ -652,7 +793,10 @@ scan_stream_kernel(const FastParams p) {
 
         // ---- tile-local scan
         V carry[J];
-        TileScan<T, Op, J, THREADS, CHAIN>::run(e, carry, p.log2_bs, lane, warp, s_warp);
+        if constexpr (SEG)
+            TileScanSeg<T, Op, J, THREADS>::run(e, carry, sv, p.bs, lane, warp, s_warp, s_wt);
+        else
+            TileScan<T, Op, J, THREADS, CHAIN>::run(e, carry, p.log2_bs, lane, warp, s_warp);
 
         // ---- prefix of the tile (resolved ahead of time by the look-back warps)
         if constexpr (CHAIN) {
@@ -662,8 +806,11 @@ scan_stream_kernel(const FastParams p) {
                 DBG_ADD(3, DBG_CLOCK() - w1);
             const V P = s_prefix[k % M];
             #pragma unroll
-            for (int j = 0; j < J; ++j)
-                carry[j] = R::apply(P, carry[j]);
+            for (int j = 0; j < J; ++j) {
+                // (SEG: only when the vector's block starts in front of the tile)
+                if (!SEG || sv[j] > (warp * (J * 32) + j * 32 + lane) * N)
+                    carry[j] = R::apply(P, carry[j]);
+            }
         }
 
         // ---- results: 128-bit streaming stores straight from registers
@@ -676,7 +823,22 @@ scan_stream_kernel(const FastParams p) {
             const uint32_t pvi = p.reverse ? VECS - 1 - lvi : lvi;
             const uint64_t pb = base + (uint64_t) pvi * N;
             V res[N];
-            if (p.exclusive) {
+            if constexpr (SEG) {
+                // `pre`: what precedes the vector within the block of its first element; it
+                // ends at the first block start inside the vector
+                V pre = sv[j] ? carry[j] : R::identity();
+                uint32_t pos = sv[j];
+                #pragma unroll
+                for (int kk = 0; kk < N; ++kk) {
+                    if (pos == 0)
+                        pre = R::identity();
+                    if (p.exclusive)
+                        res[kk] = pos == 0 ? R::identity() : (kk == 0 ? pre : R::apply(pre, e[j][kk - 1]));
+                    else
+                        res[kk] = R::apply(pre, e[j][kk]);
+                    pos = pos + 1 == p.bs ? 0u : pos + 1;
+                }
+            } else if (p.exclusive) {
                 res[0] = carry[j];
                 #pragma unroll
                 for (int kk = 1; kk < N; ++kk)
@@ -761,12 +923,12 @@ template <int THREADS_, int J_, int S_, int LB_ = 2, int LBW_ = 1> struct Geom {
 };
 using DefaultGeom = Geom<512, 4, 3, 1, B200_SCAN_LBW>;
 
-template <typename T, int Op, bool CHAIN, typename G>
+template <typename T, int Op, bool CHAIN, typename G, bool SEG = false>
 static int launch_stream(const ScanCall &c, FastParams &p) {
     using V = typename ValueOf<T>::type;
     constexpr size_t SMEM = (size_t) G::S * G::THREADS * G::J * 16;
     constexpr int BLOCK = G::THREADS + (CHAIN ? 32 + 32 * G::LB : 0);
-    auto kernel = scan_stream_kernel<T, Op, G::J, G::S, G::THREADS, CHAIN, CHAIN ? G::LB : 0, CHAIN ? G::LBW : 1>;
+    auto kernel = scan_stream_kernel<T, Op, G::J, G::S, G::THREADS, CHAIN, CHAIN ? G::LB : 0, CHAIN ? G::LBW : 1, SEG>;
 
     // per device: opt in to the dynamic shared memory size, query residency
     static std::atomic<int> occ_cache[64];
@@ -851,6 +1013,13 @@ template <typename T, int Op, typename G> static int launch_fast_g(const ScanCal
         uint32_t tps = (uint32_t) (c.bs / TILE);
         p.seg_mask = tps - 1;
         p.tile_off = c.reverse ? (tps - p.ntiles % tps) % tps : 0;
+    } else if (c.bs >= 2 && c.bs <= 0xffffffffull && !c.carry_in && !c.carry_out && !c.seeds) {
+        // any other block size: chained tiles with block starts at arbitrary elements
+        p.bs = (uint32_t) c.bs;
+        p.off = c.reverse ? (uint32_t) ((c.bs - ((uint64_t) p.ntiles * TILE) % c.bs) % c.bs) : 0u;
+        p.seg_mask = 0xffffffffu;
+        *handled = true;
+        return launch_stream<T, Op, true, G, true>(c, p);
     } else {
         return B200_OK;
     }

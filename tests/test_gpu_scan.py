@@ -236,6 +236,53 @@ def test_prefix_streaming_paths(dr, O, tname):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("tname", ["u32", "i64"])
+def test_prefix_streaming_odd_blocks(dr, O, tname):
+    """SEG mode of scan_fast.cu: block sizes that are not powers of two -- smaller than a
+    vector, around a tile (8192 / 4096 elements), multiples of a tile, larger than many
+    tiles -- at sizes of several tiles per CTA, ragged tails, every direction, in place."""
+    bad = []
+    for size in ((1 << 22) + 12345, 2500001):
+        x = int_input(tname, size)
+        for bs in (3, 5, 6, 100, 1000, 4095, 4097, 8191, 8193, 3 * 8192, 100000, 1234567, size - 1):
+            for opn, excl, rev in (("add", 0, 0), ("add", 1, 0), ("add", 1, 1), ("max", 0, 1)):
+                got = run_scan(dr, VT[tname], OP[opn], x, bs, excl, rev, inplace=(bs == 100))
+                ref = O.block_prefix_reduce(VT[tname], OP[opn], x, bs, excl, rev)
+                if not np.array_equal(got, ref):
+                    bad.append((size, bs, opn, excl, rev, int(np.flatnonzero(got != ref)[0])))
+    assert not bad, bad
+
+
+def test_prefix_streaming_odd_blocks_float(dr, O):
+    bad = []
+    size = (1 << 21) + 77
+    for tname, tol in (("f32", 1e-5), ("f64", 1e-12)):
+        dt = oracle.NP_OF_VT[VT[tname]]
+        x = f32_input(size).astype(dt)
+        for bs in (3, 100, 1000, 8193, 100000):
+            for excl, rev in ((0, 0), (1, 0), (1, 1)):
+                got = run_scan(dr, VT[tname], OP["add"], x, bs, excl, rev)
+                ref = O.block_prefix_reduce(VT[tname], OP["add"], x, bs, excl, rev, wide=True)
+                sel = ref != 0
+                err = rel_err(got[sel], ref[sel])
+                if err > tol or not np.all(got[~sel] == 0):
+                    bad.append((tname, bs, excl, rev, err))
+            got = run_scan(dr, VT[tname], OP["min"], x, bs, 0, 1)
+            if not np.array_equal(got, O.block_prefix_reduce(VT[tname], OP["min"], x, bs, 0, 1)):
+                bad.append((tname, bs, "min"))
+    x = (f32_input(1 << 18) * 0.01).astype(np.float16)
+    for bs in (3, 1000, 20000):
+        got = run_scan(dr, VT["f16"], OP["add"], x, bs, 0, 0).astype(np.float64)
+        ref = O.block_prefix_reduce(VT["f16"], OP["add"], x, bs, 0, 0, wide=True).astype(np.float64)
+        sel = ref != 0
+        if rel_err(got[sel], ref[sel]) > 2.0 ** -10:
+            bad.append(("f16", bs, rel_err(got[sel], ref[sel])))
+        got = run_scan(dr, VT["f16"], OP["max"], x, bs, 1, 1)
+        if not np.array_equal(got, O.block_prefix_reduce(VT["f16"], OP["max"], x, bs, 1, 1)):
+            bad.append(("f16", bs, "max"))
+    assert not bad, bad
+
+
 def test_prefix_streaming_float_types(dr, O):
     # f32 / f64 / f16 through the streaming kernels; tolerances as in test_prefix_float
     bad = []

@@ -54,7 +54,7 @@ def main():
     for bs in [1, 2, 4, 16, 128, 256, 1024, 4096, 1 << 16, 1 << 20, n] if on("reduce") else []:
         ms = timeit(lambda: dr.jit_block_reduce(CUDA, F32, ADD, n, bs, x, out))
         report(f"block_reduce f32 bs={bs}", ms, 4 * n * (1 + 1 / bs))
-    for bs in [1, 2, 16, 128, 256, 1024, 4096, 8192, 1 << 16, n] if on("scan") else []:
+    for bs in [1, 2, 16, 128, 256, 1024, 4096, 8192, 1 << 16, n, 3, 100, 1000, 100000, 3 << 20] if on("scan") else []:
         ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 1, 0, x, out))
         report(f"prefix f32 excl bs={bs}", ms, 8 * n if bs > 1 else 4 * n)
     xi = x.view(torch.int32)
