@@ -243,11 +243,17 @@ B200_DEVICE uint32_t seg_advance(uint32_t pos, uint32_t delta, uint32_t bs) {
 /// since the nearest block start INSIDE the vector (or since the vector's start), carry[j] the
 /// reduction of the elements of this tile in front of the vector that belong to the block of
 /// its first element.  It applies to the elements in front of the vector's first block start.
-template <typename T, int Op, int J, int THREADS> struct TileScanSeg {
+/// ONE: bs >= N, i.e. a vector contains at most one block start -- element h[j] (N: none).
+template <typename T, int Op, int J, int THREADS, bool ONE> struct TileScanSeg {
     using V = typename ValueOf<T>::type;
     using R = Red<V, Op>;
     static constexpr int N = VecInfo<T>::N;
     static constexpr int WARPS = THREADS / 32;
+
+    /// First block start inside a vector whose first element sits at position `sv` (ONE)
+    static B200_DEVICE uint32_t first_head(uint32_t sv, uint32_t bs) {
+        return sv == 0 ? 0u : min(bs - sv, (uint32_t) N);
+    }
 
     static B200_DEVICE void run(V (&e)[J][N], V (&carry)[J], const uint32_t (&sv)[J], uint32_t bs, uint32_t lane,
                                 uint32_t warp, V *s_warp, uint32_t *s_wt) {
@@ -255,26 +261,39 @@ template <typename T, int Op, int J, int THREADS> struct TileScanSeg {
         uint32_t t[J];
         #pragma unroll
         for (int j = 0; j < J; ++j) {
-            uint32_t pos = sv[j];
-            #pragma unroll
-            for (int k = 1; k < N; ++k) {
-                pos = pos + 1 == bs ? 0u : pos + 1;
-                if (pos != 0)
-                    e[j][k] = R::apply(e[j][k - 1], e[j][k]);
+            if constexpr (ONE) {
+                const uint32_t h = first_head(sv[j], bs);
+                #pragma unroll
+                for (int k = 1; k < N; ++k)
+                    if ((uint32_t) k != h)
+                        e[j][k] = R::apply(e[j][k - 1], e[j][k]);
+                t[j] = h < (uint32_t) N ? N - h : sv[j] + N;
+            } else {
+                uint32_t pos = sv[j];
+                #pragma unroll
+                for (int k = 1; k < N; ++k) {
+                    pos = pos + 1 == bs ? 0u : pos + 1;
+                    if (pos != 0)
+                        e[j][k] = R::apply(e[j][k - 1], e[j][k]);
+                }
+                t[j] = pos + 1;
             }
-            t[j] = pos + 1;
         }
-        // ---- inside a row: the vector d lanes down belongs to my block iff t > d * N
+        // ---- inside a row: the vector d lanes down belongs to my block iff t > d * N,
+        // i.e. iff d <= reach = min(lane, (t - 1) / N)
         V a[J];
+        uint32_t reach[J];
         #pragma unroll
-        for (int j = 0; j < J; ++j)
+        for (int j = 0; j < J; ++j) {
             a[j] = e[j][N - 1];
+            reach[j] = min(lane, (t[j] - 1) / (uint32_t) N);
+        }
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             #pragma unroll
             for (int j = 0; j < J; ++j) {
                 V up = shfl_up(a[j], d);
-                if (lane >= (uint32_t) d && t[j] > (uint32_t) (d * N))
+                if (reach[j] >= (uint32_t) d)
                     a[j] = R::apply(up, a[j]);
             }
         }
@@ -294,24 +313,55 @@ template <typename T, int Op, int J, int THREADS> struct TileScanSeg {
                 carry[j] = R::apply(run, carry[j]);
             run = tr > 32u * N ? R::apply(run, rt) : rt;
         }
-        // ---- across warps
+        // ---- across warps: the tail of the last warp in front of this one that contains a
+        // block start, and all of the warps between the two
         if (lane == 0) {
             s_warp[warp] = run;
             s_wt[warp] = tr;
         }
         compute_sync<THREADS>();
-        V wc = R::identity();
-        #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const V wv = s_warp[w];
-            const uint32_t wt = s_wt[w];
-            if ((uint32_t) w < warp)
-                wc = wt > (uint32_t) (J * 32 * N) ? R::apply(wc, wv) : wv;
-        }
+        static_assert(WARPS <= 32, "one lane per warp");
+        const bool mine = lane < warp;
+        const V wv = mine ? s_warp[lane] : R::identity();
+        const uint32_t heads = __ballot_sync(FULL_MASK, mine && s_wt[lane] <= (uint32_t) (J * 32 * N));
+        const uint32_t from = heads ? 31u - (uint32_t) __clz((int) heads) : 0u;
+        const V wc = warp_reduce<V, Op>(lane >= from ? wv : R::identity());
         #pragma unroll
         for (int j = 0; j < J; ++j)
             if (sv[j] > (j * 32 + lane) * N) // ... in front of this warp's rows
                 carry[j] = R::apply(wc, carry[j]);
+    }
+
+    /// Results of vector j from e / carry (after the tile's prefix has been folded into carry)
+    static B200_DEVICE void results(const V (&e)[N], V carry, uint32_t sv, uint32_t bs, bool exclusive, V (&res)[N]) {
+        // `pre`: what precedes the vector within the block of its first element; it ends at the
+        // first block start inside the vector
+        if constexpr (ONE) {
+            const uint32_t h = first_head(sv, bs);
+            #pragma unroll
+            for (int kk = 0; kk < N; ++kk) {
+                const bool front = (uint32_t) kk < h; // in front of the block start: continues `carry`
+                if (!exclusive)
+                    res[kk] = front ? R::apply(carry, e[kk]) : e[kk];
+                else if (kk == 0)
+                    res[kk] = front ? carry : R::identity();
+                else
+                    res[kk] = (uint32_t) kk == h ? R::identity() : (front ? R::apply(carry, e[kk - 1]) : e[kk - 1]);
+            }
+        } else {
+            V pre = sv ? carry : R::identity();
+            uint32_t pos = sv;
+            #pragma unroll
+            for (int kk = 0; kk < N; ++kk) {
+                if (pos == 0)
+                    pre = R::identity();
+                if (exclusive)
+                    res[kk] = pos == 0 ? R::identity() : (kk == 0 ? pre : R::apply(pre, e[kk - 1]));
+                else
+                    res[kk] = R::apply(pre, e[kk]);
+                pos = pos + 1 == bs ? 0u : pos + 1;
+            }
+        }
     }
 };
 
@@ -793,9 +843,13 @@ scan_stream_kernel(const FastParams p) {
 
         // ---- tile-local scan
         V carry[J];
-        if constexpr (SEG)
-            TileScanSeg<T, Op, J, THREADS>::run(e, carry, sv, p.bs, lane, warp, s_warp, s_wt);
-        else
+        const bool seg_one = SEG && p.bs >= (uint32_t) N; // at most one block start per vector (CTA-uniform)
+        if constexpr (SEG) {
+            if (seg_one)
+                TileScanSeg<T, Op, J, THREADS, true>::run(e, carry, sv, p.bs, lane, warp, s_warp, s_wt);
+            else
+                TileScanSeg<T, Op, J, THREADS, false>::run(e, carry, sv, p.bs, lane, warp, s_warp, s_wt);
+        } else
             TileScan<T, Op, J, THREADS, CHAIN>::run(e, carry, p.log2_bs, lane, warp, s_warp);
 
         // ---- prefix of the tile (resolved ahead of time by the look-back warps)
@@ -824,20 +878,10 @@ scan_stream_kernel(const FastParams p) {
             const uint64_t pb = base + (uint64_t) pvi * N;
             V res[N];
             if constexpr (SEG) {
-                // `pre`: what precedes the vector within the block of its first element; it
-                // ends at the first block start inside the vector
-                V pre = sv[j] ? carry[j] : R::identity();
-                uint32_t pos = sv[j];
-                #pragma unroll
-                for (int kk = 0; kk < N; ++kk) {
-                    if (pos == 0)
-                        pre = R::identity();
-                    if (p.exclusive)
-                        res[kk] = pos == 0 ? R::identity() : (kk == 0 ? pre : R::apply(pre, e[j][kk - 1]));
-                    else
-                        res[kk] = R::apply(pre, e[j][kk]);
-                    pos = pos + 1 == p.bs ? 0u : pos + 1;
-                }
+                if (seg_one)
+                    TileScanSeg<T, Op, J, THREADS, true>::results(e[j], carry[j], sv[j], p.bs, p.exclusive, res);
+                else
+                    TileScanSeg<T, Op, J, THREADS, false>::results(e[j], carry[j], sv[j], p.bs, p.exclusive, res);
             } else if (p.exclusive) {
                 res[0] = carry[j];
                 #pragma unroll
