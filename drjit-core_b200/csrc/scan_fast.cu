@@ -337,16 +337,19 @@ template <typename T, int Op, int J, int THREADS, bool ONE> struct TileScanSeg {
         // `pre`: what precedes the vector within the block of its first element; it ends at the
         // first block start inside the vector
         if constexpr (ONE) {
+            // elements in front of the block start continue `carry`; an exclusive result is the
+            // inclusive one of the element before, or the identity at the block start
             const uint32_t h = first_head(sv, bs);
+            V incl[N];
+            #pragma unroll
+            for (int kk = 0; kk < N; ++kk)
+                incl[kk] = (uint32_t) kk < h ? R::apply(carry, e[kk]) : e[kk];
             #pragma unroll
             for (int kk = 0; kk < N; ++kk) {
-                const bool front = (uint32_t) kk < h; // in front of the block start: continues `carry`
                 if (!exclusive)
-                    res[kk] = front ? R::apply(carry, e[kk]) : e[kk];
-                else if (kk == 0)
-                    res[kk] = front ? carry : R::identity();
+                    res[kk] = incl[kk];
                 else
-                    res[kk] = (uint32_t) kk == h ? R::identity() : (front ? R::apply(carry, e[kk - 1]) : e[kk - 1]);
+                    res[kk] = (uint32_t) kk == h ? R::identity() : (kk == 0 ? carry : incl[kk - 1]);
             }
         } else {
             V pre = sv ? carry : R::identity();
