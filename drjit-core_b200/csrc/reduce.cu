@@ -249,6 +249,10 @@ reduce_rows_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size,
 
 /// Arbitrary small blocks (block bytes < 512): each CTA owns 'nb' whole blocks,
 /// staged in shared memory.  Dynamic shared memory: (cap + 2 * N) elements.
+/// The blocks are then reduced by groups of 2^log2_group lanes each (one lane per block
+/// when log2_group == 0: consecutive lanes read shared memory bs elements apart, which is
+/// conflict free for the block sizes the launcher sends here).  All indices inside a tile
+/// are 32 bit; tiles that lie inside the array take loads without bounds checks.
 template <typename T, int Op>
 __global__ void __launch_bounds__(REDUCE_THREADS)
 reduce_tiles_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size,
@@ -271,40 +275,92 @@ reduce_tiles_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t size
     // offset of element 'start' inside the staged tile
     const uint32_t shift = (uint32_t) (start + mis - q_first * N);
 
-    for (uint32_t i = threadIdx.x; i < nvec; i += REDUCE_THREADS) {
-        uint64_t q = q_first + i, v0 = q * N;
-        Vec16<T> v;
-        if (v0 >= mis && v0 + N <= size + mis) {
-            v.raw = ld_stream(in + (v0 - mis)); // may straddle into a neighbour tile
-        } else {
-            #pragma unroll
-            for (int k = 0; k < N; ++k) {
-                uint64_t vi = v0 + k;
-                v.elem[k] = (vi >= mis && vi < size + mis) ? in[vi - mis] : T();
+    if (q_first * N >= mis && (q_last + 1) * N <= size + mis) {
+        // (vectors may straddle into a neighbour tile)
+        const uint4 *src = (const uint4 *) (in + (q_first * N - mis));
+        for (uint32_t i = threadIdx.x; i < nvec; i += REDUCE_THREADS)
+            tile_smem[i] = ld_stream(src + i);
+    } else {
+        for (uint32_t i = threadIdx.x; i < nvec; i += REDUCE_THREADS) {
+            uint64_t q = q_first + i, v0 = q * N;
+            Vec16<T> v;
+            if (v0 >= mis && v0 + N <= size + mis) {
+                v.raw = ld_stream(in + (v0 - mis));
+            } else {
+                #pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    uint64_t vi = v0 + k;
+                    v.elem[k] = (vi >= mis && vi < size + mis) ? in[vi - mis] : T();
+                }
             }
+            tile_smem[i] = v.raw;
         }
-        tile_smem[i] = v.raw;
     }
     __syncthreads();
 
-    const uint32_t group = 1u << log2_group, groups_per_warp = 32 >> log2_group;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sub = lane & (group - 1), grp = lane >> log2_group;
-    constexpr uint32_t WARPS = REDUCE_THREADS / 32;
-
-    for (uint32_t b0 = warp * groups_per_warp; b0 < nb_tile; b0 += WARPS * groups_per_warp) {
-        uint32_t b = b0 + grp;
-        V acc = R::identity();
-        if (b < nb_tile) {
-            uint64_t bstart = start + (uint64_t) b * bs;
-            uint32_t len = (uint32_t) min((uint64_t) bs, size - bstart);
+    const uint32_t tail = (uint32_t) (end - start) - (nb_tile - 1) * bs; // length of the tile's last block
+    out += blk0;
+    if (log2_group == 0) {
+        // one thread per block
+        for (uint32_t b = threadIdx.x; b < nb_tile; b += REDUCE_THREADS) {
             const T *src = tile + shift + b * bs;
-            for (uint32_t k = sub; k < len; k += group)
+            const uint32_t len = b + 1 < nb_tile ? bs : tail;
+            V acc = to_value<T>(src[0]);
+            #pragma unroll 4
+            for (uint32_t k = 1; k < len; ++k)
                 acc = R::apply(acc, to_value<T>(src[k]));
+            out[b] = from_value<T>(acc);
         }
-        acc = warp_reduce<V, Op>(acc, (int) group);
-        if (b < nb_tile && sub == 0)
-            out[blk0 + b] = from_value<T>(acc);
+        return;
+    }
+
+    // groups of G lanes per block (G a compile-time constant: the loops unroll)
+    auto by_groups = [&](auto tag) {
+        constexpr uint32_t LOG2_G = decltype(tag)::value, G = 1u << LOG2_G, GROUPS_PER_WARP = 32 >> LOG2_G;
+        constexpr uint32_t WARPS = REDUCE_THREADS / 32;
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t sub = lane & (G - 1), grp = lane >> LOG2_G;
+        // BU blocks per group and step: their shuffle reductions are independent chains
+        constexpr uint32_t BU = 4;
+        for (uint32_t b0 = warp * GROUPS_PER_WARP; b0 < nb_tile; b0 += WARPS * GROUPS_PER_WARP * BU) {
+            V acc[BU];
+            #pragma unroll
+            for (uint32_t u = 0; u < BU; ++u) {
+                const uint32_t b = b0 + u * WARPS * GROUPS_PER_WARP + grp;
+                acc[u] = R::identity();
+                if (b < nb_tile) {
+                    const uint32_t len = b + 1 < nb_tile ? bs : tail;
+                    const T *src = tile + shift + b * bs;
+                    // (a block has fewer than 2 * G elements, except for G == 32: fewer than 512 bytes)
+                    constexpr uint32_t ROUNDS = G == 32 ? (uint32_t) ((512 / sizeof(T) + 31) / 32) : 2u;
+                    #pragma unroll
+                    for (uint32_t r = 0; r < ROUNDS; ++r) {
+                        const uint32_t k = sub + r * G;
+                        if (k < len)
+                            acc[u] = R::apply(acc[u], to_value<T>(src[k]));
+                    }
+                }
+            }
+            #pragma unroll
+            for (uint32_t d = G >> 1; d > 0; d >>= 1) {
+                #pragma unroll
+                for (uint32_t u = 0; u < BU; ++u)
+                    acc[u] = R::apply(acc[u], shfl_xor(acc[u], (int) d));
+            }
+            #pragma unroll
+            for (uint32_t u = 0; u < BU; ++u) {
+                const uint32_t b = b0 + u * WARPS * GROUPS_PER_WARP + grp;
+                if (b < nb_tile && sub == 0)
+                    out[b] = from_value<T>(acc[u]);
+            }
+        }
+    };
+    switch (log2_group) {
+        case 1: by_groups(std::integral_constant<uint32_t, 1>()); break;
+        case 2: by_groups(std::integral_constant<uint32_t, 2>()); break;
+        case 3: by_groups(std::integral_constant<uint32_t, 3>()); break;
+        case 4: by_groups(std::integral_constant<uint32_t, 4>()); break;
+        default: by_groups(std::integral_constant<uint32_t, 5>()); break;
     }
 }
 
@@ -588,10 +644,19 @@ template <typename T, int Op> static int launch_block_reduce(const ReduceCall &c
     }
 
     if (block_bytes < 512) {
-        constexpr uint32_t CAP = 16384 / sizeof(T);
+        constexpr uint32_t CAP = 32768 / sizeof(T);
         uint32_t nb = (uint32_t) (CAP / bs);
         uint32_t group = 1, log2_group = 0;
         while (group * 2 <= bs && group < 32) { group *= 2; log2_group++; }
+        // short blocks whose lanes would not collide in shared memory (consecutive blocks start
+        // an odd number of 32-bit words apart, or two words for 6- and 10-element blocks of
+        // 4-byte types ...): one thread per block
+        {
+            const uint32_t words2 = (uint32_t) (bs * sizeof(T) / 2); // block stride in half words
+            const uint32_t conflict = words2 % 2 ? 1u : std::min(32u, (words2 / 2) & (~(words2 / 2) + 1u));
+            if (bs <= 32 && conflict <= 2)
+                group = 1, log2_group = 0;
+        }
         uint64_t ntiles = ceil_div(nblocks, nb);
         if (ntiles > 0x7fffffffull)
             return fail(B200_ERR_INVALID, "jit_block_reduce(): array too large!");

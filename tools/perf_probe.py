@@ -51,7 +51,7 @@ def main():
 
     ms = timeit(lambda: out.copy_(x))
     report("torch copy (r+w)", ms, 8 * n)
-    for bs in [1, 2, 4, 16, 128, 256, 1024, 4096, 1 << 16, 1 << 20, n] if on("reduce") else []:
+    for bs in [1, 2, 4, 16, 128, 256, 1024, 4096, 1 << 16, 1 << 20, n, 3, 7, 100, 1000, 100000, 3 << 20] if on("reduce") else []:
         ms = timeit(lambda: dr.jit_block_reduce(CUDA, F32, ADD, n, bs, x, out))
         report(f"block_reduce f32 bs={bs}", ms, 4 * n * (1 + 1 / bs))
     for bs in [1, 2, 16, 128, 256, 1024, 4096, 8192, 1 << 16, n, 3, 100, 1000, 100000, 3 << 20] if on("scan") else []:
