@@ -65,6 +65,7 @@ struct FastParams {
     uint32_t log2_bs;    // POW2: log2(block_size)
     uint32_t seg_mask;   // CHAIN: tiles per block - 1 (0xffffffff: one block)
     uint32_t tile_off;   // CHAIN: phase of the block grid in logical tile space
+    uint32_t log2_group; // CHAIN: a ticket stands for 2^log2_group neighbouring tiles (one global look-back per group)
     uint32_t bs;         // SEG: block size; logical element I starts a block iff (I + off) % bs == 0
     uint32_t off;        // SEG: phase of the block grid in logical element space
     uint32_t exclusive;
@@ -401,6 +402,7 @@ scan_stream_kernel(const FastParams p) {
     __shared__ uint32_t s_mseg[M];   // SEG: bit 0 = the tile contains a block start, bit 1 = it begins with one
     __shared__ uint32_t s_wt[WARPS];
     __shared__ V s_total[M];
+    __shared__ V s_local[M];   // aggregate of the tiles of the same group in front of the tile
     __shared__ V s_prefix[M];
     __shared__ V s_warp[WARPS];
 
@@ -433,6 +435,24 @@ scan_stream_kernel(const FastParams p) {
         }
     };
 
+    // CHAIN: a ticket stands for a GROUP of 2^log2_group neighbouring tiles, which this CTA takes one after
+    // the other.  Every tile still publishes its own aggregate the moment it has landed, but only the
+    // group's first tile looks back through global memory: the others continue from the aggregates the
+    // CTA already holds, so the look-back warp -- one global look-back per tile kept it busy 90 % of the
+    // time -- stops being the bottleneck.  (One DESCRIPTOR per group was measured as well and is slower,
+    // 0.47 vs 0.39 ms at 2^28: the group's aggregate is complete one ring turn later and every successor
+    // polls that long.)
+    const uint32_t glog = CHAIN ? p.log2_group : 0u, gmask = (1u << glog) - 1u;
+    uint32_t tk_next = 0, tk_left = 0; // (thread 0)
+    auto next_tile = [&]() -> uint32_t {
+        if (tk_left == 0) {
+            tk_next = atomicAdd(p.ticket, 1u) << glog;
+            tk_left = gmask + 1;
+        }
+        --tk_left;
+        return tk_next++;
+    };
+
     if (tid == 0) {
         #pragma unroll
         for (int s = 0; s < S; ++s)
@@ -444,7 +464,7 @@ scan_stream_kernel(const FastParams p) {
         }
         mbar_fence_init();
         for (uint32_t i = 0; i < (uint32_t) S; ++i)
-            issue(i, atomicAdd(p.ticket, 1u));
+            issue(i, next_tile());
     }
     __syncthreads();
 
@@ -513,6 +533,7 @@ scan_stream_kernel(const FastParams p) {
         // this CTA.
         if (warp == WARPS) {
             int none_seen = 0;
+            V gacc = R::identity(); // lane 0: aggregate of the current group so far
             for (uint32_t k = 0;; ++k) {
                 const uint32_t slot = k % S;
                 long long c0 = DBG_CLOCK();
@@ -611,9 +632,12 @@ scan_stream_kernel(const FastParams p) {
                 const V total = warp_reduce<V, Op>(acc[0]);
                 if (lane == 0) {
                     // (SEG: a tile with a block start inside publishes its tail as a prefix)
+                    const uint32_t g = tile & gmask;
                     const bool first = SEG ? tile == 0 || (seg_bits & 1u) : ((tile + p.tile_off) & p.seg_mask) == 0;
                     if constexpr (SEG)
                         s_mseg[m] = seg_bits;
+                    s_local[m] = g ? gacc : R::identity();
+                    gacc = g ? R::apply(gacc, total) : total;
                     if (first) {
                         V P = R::identity();
                         if (p.carry_in)
@@ -654,6 +678,7 @@ scan_stream_kernel(const FastParams p) {
         // 32 descriptors, publish the inclusive prefix and hand the exclusive
         // one to the compute warps.
         if (warp > WARPS) {
+            V GP = R::identity(); // exclusive prefix of the current group (groups need LB == 1)
             for (uint32_t k = warp - (WARPS + 1);; k += LB) {
                 const uint32_t m = k % M;
                 long long c0 = DBG_CLOCK();
@@ -667,18 +692,25 @@ scan_stream_kernel(const FastParams p) {
                 const V total = s_total[m];
                 // SEG: no prefix to find when the tile begins with a block start; nothing to
                 // publish when it contains one (the aggregate warp has done that already)
+                const uint32_t g = tile & gmask;
                 const bool first = SEG ? tile == 0 || (s_mseg[m] & 2u) : ((tile + p.tile_off) & p.seg_mask) == 0;
                 V P = R::identity();
                 if (p.seeds) {
                     // SEEDED: the caller knows every tile's exclusive prefix (tile sums
                     // from a reduce pass it had to make anyway) -- no chain, no polling
                     P = ((const V *) p.seeds)[p.reverse ? p.ntiles - 1 - tile : tile];
-                } else if (first) {
-                    if (p.carry_in)
-                        P = *(const V *) p.carry_in;
                 } else {
-                    P = look_back(tile);
-                    if (lane == 0 && !(SEG && (s_mseg[m] & 1u)))
+                    if (g == 0) {
+                        // only the group's first tile looks back through global memory ...
+                        GP = R::identity();
+                        if (!first)
+                            GP = look_back(tile);
+                        else if (p.carry_in)
+                            GP = *(const V *) p.carry_in;
+                    }
+                    // ... the others continue from the aggregates this CTA holds
+                    P = g ? R::apply(GP, s_local[m]) : GP;
+                    if (!first && lane == 0 && !(SEG && (s_mseg[m] & 1u)))
                         Desc<V>::publish(p.desc, tile, DESC_PREFIX, R::apply(P, total));
                 }
                 if (p.cyc.world) {
@@ -779,7 +811,7 @@ scan_stream_kernel(const FastParams p) {
         // only after the tile has been read (hides the atomic's round trip)
         uint32_t next_ticket = 0;
         if (tid == 0)
-            next_ticket = atomicAdd(p.ticket, 1u);
+            next_ticket = next_tile();
         long long w0 = DBG_CLOCK();
         mbar_wait(&s_full[slot], parity);
         if (tid == 32)
@@ -947,6 +979,19 @@ static int scan_path() {
     return path;
 }
 
+/// Cap of log2(tiles per ticket) of the chained scan over blocks of several tiles (development switch
+/// B200_SCAN_GROUP)
+static uint32_t scan_group_log2() {
+    static int lg = -1;
+    if (lg < 0) {
+        const char *s = getenv("B200_SCAN_GROUP");
+        lg = s ? atoi(s) : 4;
+        if (lg < 0 || lg > 8)
+            lg = 4;
+    }
+    return (uint32_t) lg;
+}
+
 template <typename K> static int prepare_kernel(K kernel, int threads, size_t smem, int *occupancy) {
     if (smem > 48 * 1024)
         B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1071,6 +1116,16 @@ template <typename T, int Op, typename G> static int launch_fast_g(const ScanCal
         return B200_OK;
     }
     *handled = true;
+    if (chain && !c.cyclic && !c.seeds && G::LB == 1 && p.seg_mask != 0xffffffffu) {
+        // A block of up to 2^cap tiles is taken by ONE CTA, tile after tile (a "group"): no global look-back
+        // at all (2^28 fp32, blocks of 2 / 4 / 8 / 16 tiles: 0.37-0.38 ms -> 0.34 / 0.34 / 0.35 / 0.36 ms).
+        // Groups that are only a part of their block lose (a tile's predecessors then land one ring turn
+        // later and every look-back waits that long; blocks of 32 tiles in groups of 16: 0.38 -> 0.45 ms, the
+        // whole array in groups of 2 / 4: 0.39 -> 0.44 / 0.48 ms), so larger blocks keep single tiles.
+        const uint32_t lg = log2i(p.seg_mask + 1);
+        if (lg <= scan_group_log2() && (p.tile_off & p.seg_mask) == 0)
+            p.log2_group = lg;
+    }
     if (chain)
         return launch_stream<T, Op, true, G>(c, p);
     return launch_stream<T, Op, false, G>(c, p);

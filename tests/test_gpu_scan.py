@@ -227,12 +227,30 @@ def test_prefix_streaming_paths(dr, O, tname):
     sizes = [(1 << 22) + 12345, 3 * (1 << 20), 2500001]
     for size in sizes:
         x = int_input(tname, size)
-        for bs in (2, 4, 8, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 1 << 16, 1 << 20, size):
+        for bs in (2, 4, 8, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 18,
+                   1 << 20, size):
             for opn, excl, rev in (("add", 0, 0), ("add", 1, 1), ("max", 1, 0), ("min", 0, 1)):
                 got = run_scan(dr, VT[tname], OP[opn], x, bs, excl, rev, inplace=(bs == 64))
                 ref = O.block_prefix_reduce(VT[tname], OP[opn], x, bs, excl, rev)
                 if not np.array_equal(got, ref):
                     bad.append((size, bs, opn, excl, rev))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("tname", ["u32", "u64"])
+def test_prefix_streaming_block_groups(dr, O, tname):
+    """Blocks of 2 .. 16 tiles are scanned by one CTA each, tile after tile, without a global look-back
+    (scan_fast.cu, `log2_group`); larger blocks and ragged reverse scans keep the per-tile chain.  Sizes of
+    many groups per CTA, whole and ragged; bit-exact."""
+    bad = []
+    for size in (1 << 25, (1 << 25) + (1 << 16) + 77, 40000003):
+        x = int_input(tname, size)
+        for bs in (1 << 13, 1 << 14, 1 << 16, 1 << 17, 1 << 18):
+            for excl, rev in ((1, 0), (0, 1)):
+                got = run_scan(dr, VT[tname], OP["add"], x, bs, excl, rev)
+                ref = O.block_prefix_reduce(VT[tname], OP["add"], x, bs, excl, rev)
+                if not np.array_equal(got, ref):
+                    bad.append((size, bs, excl, rev))
     assert not bad, bad
 
 

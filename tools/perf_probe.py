@@ -57,6 +57,11 @@ def main():
     for bs in [1, 2, 16, 128, 256, 1024, 4096, 8192, 1 << 16, n, 3, 100, 1000, 100000, 3 << 20] if on("scan") else []:
         ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 1, 0, x, out))
         report(f"prefix f32 excl bs={bs}", ms, 8 * n if bs > 1 else 4 * n)
+    for bs in [1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 20, 1 << 24] if "scan_seg" in want else []:
+        ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 1, 0, x, out))
+        report(f"prefix f32 excl bs={bs}", ms, 8 * n)
+        ms = timeit(lambda: dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 0, 1, x, out))
+        report(f"prefix f32 incl reverse bs={bs}", ms, 8 * n)
     xi = x.view(torch.int32)
     oi = out.view(torch.int32)
     if on("scan"):
