@@ -254,6 +254,60 @@ def test_prefix_streaming_block_groups(dr, O, tname):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("tname", ["u32", "i32", "u64", "i64"])
+def test_prefix_two_stream_chain(dr, O, tname):
+    """scan_ahead_kernel (scan_fast.cu): whole arrays and blocks of more than 16 tiles, from 1024 tiles on --
+    a reduce stream ahead of the scan stream, one prefix stream over the tile aggregates.  Ragged ends (reverse:
+    the block grid is out of phase with the tiles, tile 0 is not a block start), in place, every operation,
+    blocks of few tiles with a ragged reverse end (no groups).  Bit-exact."""
+    bad = []
+    tile = 32768 // np.dtype(int_input(tname, 1).dtype).itemsize
+    for size in (1024 * tile, 1500 * tile + 12345, 3000 * tile + 1):
+        x = int_input(tname, size)
+        for bs in (size, 32 * tile, 64 * tile, 2 * tile):
+            for opn, excl, rev in (("add", 1, 0), ("add", 0, 1), ("max", 1, 1), ("min", 0, 0), ("or_", 1, 1)):
+                if opn == "or_" and tname in ("i32", "i64"):
+                    continue
+                got = run_scan(dr, VT[tname], OP[opn], x, bs, excl, rev, inplace=(opn == "max"))
+                ref = O.block_prefix_reduce(VT[tname], OP[opn], x, bs, excl, rev)
+                if not np.array_equal(got, ref):
+                    bad.append((size, bs, opn, excl, rev))
+    assert not bad, bad
+
+
+def test_prefix_two_stream_chain_carry_and_float(dr, O):
+    bad = []
+    size = 1100 * 8192 + 77
+    x = u32_input(size)
+    for excl, rev in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        carry = to_dev(np.array([12345], dtype=np.uint32))
+        cout = empty_dev(1, np.uint32)
+        d_out = empty_dev(size, np.uint32)
+        dr.prefix_reduce_carry(VT["u32"], OP["add"], size, excl, rev, to_dev(x), d_out, carry, cout)
+        ref = (O.block_prefix_reduce(VT["u32"], OP["add"], x, size, excl, rev) + np.uint32(12345)).astype(np.uint32)
+        total = np.uint32(int(x.sum(dtype=np.uint64) + 12345) & 0xFFFFFFFF)
+        if not np.array_equal(to_host(d_out, np.uint32), ref) or to_host(cout, np.uint32)[0] != total:
+            bad.append((excl, rev))
+    assert not bad, bad
+    # fp32 / fp64 / fp16: every prefix against an fp64 accumulation
+    xf = f32_input(size)
+    for dt, vt, tol in ((np.float32, "f32", 1e-5), (np.float64, "f64", 1e-12)):
+        xs = xf.astype(dt)
+        for excl, rev in ((1, 0), (0, 1)):
+            got = run_scan(dr, VT[vt], OP["add"], xs, size, excl, rev).astype(np.float64)
+            v = xs.astype(np.float64)[::-1] if rev else xs.astype(np.float64)
+            ref = np.cumsum(v)
+            if excl:
+                ref = np.concatenate(([0.0], ref[:-1]))
+            if rev:
+                ref = ref[::-1]
+            assert rel_err(got, ref) <= tol, (vt, excl, rev, rel_err(got, ref))
+        # the two-stream scan sums in a fixed order: run-to-run identical
+        a = run_scan(dr, VT[vt], OP["add"], xs, size, 1, 0)
+        b = run_scan(dr, VT[vt], OP["add"], xs, size, 1, 0)
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("tname", ["u32", "i64"])
 def test_prefix_streaming_odd_blocks(dr, O, tname):
     """SEG mode of scan_fast.cu: block sizes that are not powers of two -- smaller than a

@@ -1,8 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for d in 0 8; do
-  echo "--- B200_SCAN_DBG=$d"
-  B200_SCAN_DBG=$d timeout 300 python tools/perf_probe.py scan 2>&1 | grep prefix | grep -E "bs=26|bs=n" 
-done | tee gpurun_out/perf_probe_scan.log
-export B200_LIB_PATH=$PWD/gpurun_tuning.so
-timeout 600 python tools/tune_scan.py 0:2 0:10 2>&1 | tee gpurun_out/tune_scan.log
+timeout 400 python -m pytest tests/test_gpu_scan.py -m gpu -q --timeout 120 -p no:cacheprovider -k "two_stream or full_size or carry" > gpurun_out/test_scan.log 2>&1
+echo "tests rc=$? $(tail -1 gpurun_out/test_scan.log)" | tee gpurun_out/summary.txt
+grep -E "FAILED|Error|error|assert" gpurun_out/test_scan.log | head -20

@@ -32,6 +32,9 @@ def main():
         for bs in (2, 128, 1024, 4096, n):
             dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, bs, 1, 0, x, out)
         dr.jit_block_prefix_reduce(CUDA, U32, ADD, n, n, 1, 0, x.view(torch.int32), oi)
+    if "scan_whole" in want:
+        dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, n, 1, 0, x, out)
+        dr.jit_block_prefix_reduce(CUDA, F32, ADD, n, n, 1, 0, x, out)
     if "reduce_odd" in want:
         for bs in (3, 7, 100):
             dr.jit_block_reduce(CUDA, F32, ADD, n, bs, x, out)
