@@ -19,6 +19,8 @@
 //           (run-to-run deterministic, also for floating point).
 #include "common.cuh"
 
+#include <atomic>
+
 #include <cstdlib>
 
 namespace b200 {
@@ -683,12 +685,35 @@ template <typename T, int Op> static int launch_block_reduce(const ReduceCall &c
 
     uint64_t max_chunks = std::max<uint64_t>(1, block_bytes / iter_bytes_cta);
     uint64_t chunks = std::min(max_chunks, std::max<uint64_t>(1, ceil_div(target_teams, nblocks)));
+    // Many large blocks (the finish runs as a second kernel anyway): chunks of ~128 KiB, i.e. several
+    // teams per CTA.  With `target_teams` alone 256 blocks of 4 MiB became 1280 teams of 0.8 MiB on 1184
+    // resident CTAs -- a second wave of 96 CTAs that took as long as the first (2^28 fp32, blocks of 2^20 /
+    // 3 * 2^20 elements: 0.215 / 0.232 ms -> 0.184 / 0.186 ms).
+    static const int tune = getenv("B200_REDUCE_TUNE") ? atoi(getenv("B200_REDUCE_TUNE")) : 7; // (development switch: bit 0 / 1 the two rules below, bit 2 four teams per CTA)
+    if (nblocks > 64 && block_bytes >= (1u << 20) && (tune & 1))
+        chunks = std::min(max_chunks, std::max(chunks, ceil_div(block_bytes, (uint64_t) 128 * 1024)));
+    // Few blocks (one launch, the last CTA finishes): four teams per RESIDENT CTA, never more CTAs than
+    // that -- the partial kernel holds 5 CTAs per SM (44 registers), so the 8 teams per SM assumed above
+    // ran as 1.6 waves (whole-array reduce, 2^28 fp32: 0.184 -> 0.178 ms)
+    uint32_t resident = 0;
+    if (nblocks <= 64 && (tune & 2)) {
+        static std::atomic<int> occ_cache{0};
+        int occ = occ_cache.load(std::memory_order_relaxed);
+        if (occ == 0) {
+            B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &occ, reduce_chunks_kernel<T, Op, REDUCE_THREADS, true, U>, REDUCE_THREADS, 0));
+            occ = std::max(occ, 1);
+            occ_cache.store(occ, std::memory_order_relaxed);
+        }
+        resident = (uint32_t) (sms * occ);
+        chunks = std::min(max_chunks, std::max<uint64_t>(1, (uint64_t) ((tune & 4) ? 4 : (tune & 8) ? 1 : 2) * resident / nblocks));
+    }
     uint64_t chunk = ceil_div(bs, chunks);
     // keep chunk boundaries on 16-byte multiples relative to the block start
     chunk = ceil_div(chunk, N * 32) * (N * 32);
     chunks = ceil_div(bs, chunk);
     uint64_t nteams = nblocks * chunks;
-    uint32_t grid = (uint32_t) std::min<uint64_t>(nteams, (uint64_t) sms * 16);
+    uint32_t grid = (uint32_t) std::min<uint64_t>(nteams, resident ? (uint64_t) resident : (uint64_t) sms * 16);
 
     if (chunks == 1) {
         reduce_chunks_kernel<T, Op, REDUCE_THREADS, false, U><<<grid, REDUCE_THREADS, 0, c.stream>>>(
