@@ -1063,7 +1063,7 @@ scan_ahead_kernel(const FastParams p) {
     if (blockIdx.x == gridDim.x - 1) {
         if (warp != 0)
             return;
-        constexpr int PW = 4;
+        constexpr int PW = 8;
         V val[PW], nval[PW];
         uint32_t st[PW], nst[PW];
         auto fetch = [&](uint32_t base, V (&v)[PW], uint32_t (&s)[PW]) {
