@@ -11,6 +11,10 @@
 //   CHAIN  the whole array is one block (optionally seeded with a carry), or
 //          block_size is a power-of-two multiple of the tile: tiles are chained
 //          with decoupled look-back over 64-bit {status, value} descriptors.
+//          Blocks of 2..16 tiles are scanned by one CTA each (tile groups: no global
+//          look-back); whole arrays and larger blocks of 4-byte types, from 1024 tiles
+//          on, run as two streams (scan_ahead_kernel below: a reduce stream ahead of
+//          the scan stream, one prefix stream over the tile aggregates).
 //   SEG    any other block size: CHAIN with block boundaries at arbitrary elements.
 //          Boundaries are regular, so no head flags travel through the scan: every
 //          combine step is guarded by the distance of a vector to the most recent
@@ -968,6 +972,23 @@ scan_stream_kernel(const FastParams p) {
 }
 
 
+/// Bounded spinning for the waits of scan_ahead_kernel: traps (a sticky error, i.e. a loud failure) when a
+/// descriptor has not appeared 20 s after the first 1024 polls
+struct SpinGuard {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    B200_DEVICE void tick() {
+        if ((++spins & 1023u) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > 20ull * 1000 * 1000 * 1000)
+                __trap();
+        }
+    }
+};
+
 // ---------------------------------------------------------------- AHEAD: the chained scan as two streams
 //
 // What bounds the chained kernel above is not a throughput but a latency: the prefix of a tile exists ~3 us
@@ -1080,7 +1101,7 @@ scan_ahead_kernel(const FastParams p) {
         fetch(0, val, st);
         for (uint32_t base = 0; base < p.ntiles; base += 32 * PW) {
             // all entries of the batch must be there (the reduce stream is usually far ahead)
-            uint32_t spins = 0;
+            SpinGuard guard;
             while (true) {
                 bool missing = false;
                 #pragma unroll
@@ -1089,8 +1110,7 @@ scan_ahead_kernel(const FastParams p) {
                 if (!__any_sync(FULL_MASK, missing))
                     break;
                 __nanosleep(200);
-                if (++spins > (1u << 24))
-                    __trap();
+                guard.tick();
                 #pragma unroll
                 for (int w = 0; w < PW; ++w) {
                     const uint32_t idx = base + 32 * w + lane;
@@ -1284,22 +1304,20 @@ scan_ahead_kernel(const FastParams p) {
                     if (p.carry_in)
                         P = *(const V *) p.carry_in;
                 } else if (tile > 0) {
-                    uint32_t spins = 0;
+                    SpinGuard guard; // (a lost prefix must fail loudly, not hang)
                     while (Desc<V>::observe(p.desc, tile - 1, P) != DESC_PREFIX) {
                         __nanosleep(100);
-                        if (++spins > (1u << 25))
-                            __trap(); // (a lost prefix must fail loudly, not hang)
+                        guard.tick();
                     }
                 }
             } else if (lane == 1 && p.in == p.out) {
                 // in place: the tile must not be overwritten before the reduce stream has read it (nothing else
                 // orders the two -- the scan of a tile needs the aggregates in front of it, not its own)
                 V own;
-                uint32_t spins = 0;
+                SpinGuard guard;
                 while (Desc<V>::observe(p.desc, tile, own) == DESC_INVALID) {
                     __nanosleep(100);
-                    if (++spins > (1u << 25))
-                        __trap();
+                    guard.tick();
                 }
             }
             __syncwarp();
