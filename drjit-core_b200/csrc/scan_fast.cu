@@ -635,6 +635,7 @@ scan_stream_kernel(const FastParams p) {
                         acc[u] = R::apply(acc[u], acc[u + w]);
                 }
                 const V total = warp_reduce<V, Op>(acc[0]);
+                __syncwarp(); // every lane has read the slot before lane 0 lets the producer refill it
                 if (lane == 0) {
                     // (SEG: a tile with a block start inside publishes its tail as a prefix)
                     const uint32_t g = tile & gmask;
