@@ -1645,11 +1645,13 @@ template <typename T, int Op, typename G> static int launch_fast_g(const ScanCal
             p.log2_group = lg;
     }
     // (4-byte types: measured slower than the chained kernel for 64-bit elements, 0.51 vs 0.475 ms at 2^27)
-    if (sizeof(T) == 4 && chain && !c.cyclic && !c.seeds && p.log2_group == 0 && p.ntiles >= 1024 && scan_ahead_lag() >= 0) {
-        bool done = false;
-        int rc = launch_ahead<T, Op, G>(c, p, &done);
-        if (rc || done)
-            return rc;
+    if constexpr (sizeof(T) == 4) {
+        if (chain && !c.cyclic && !c.seeds && p.log2_group == 0 && p.ntiles >= 1024 && scan_ahead_lag() >= 0) {
+            bool done = false;
+            int rc = launch_ahead<T, Op, G>(c, p, &done);
+            if (rc || done)
+                return rc;
+        }
     }
     if (chain)
         return launch_stream<T, Op, true, G>(c, p);
