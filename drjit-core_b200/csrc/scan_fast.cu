@@ -1028,6 +1028,7 @@ scan_ahead_kernel(const FastParams p) {
     __shared__ __align__(8) uint64_t s_pref[M];   // s_prefix entry is valid
     __shared__ uint32_t s_qtile[M];
     __shared__ uint32_t s_rtile[RS];
+    __shared__ uint32_t s_role;
     __shared__ V s_prefix[M];
     __shared__ V s_warp[WARPS];
 
@@ -1068,7 +1069,12 @@ scan_ahead_kernel(const FastParams p) {
             mbar_init(&s_pref[s], 1);
         }
         mbar_fence_init();
-        if (blockIdx.x != gridDim.x - 1) { // (the last CTA runs the prefix stream)
+        // Roles are handed out in the order in which CTAs START: the first one runs the prefix stream.  Every
+        // stream a CTA may wait for is therefore owned by a CTA that is already running (the reduce and scan
+        // streams through their tickets, the prefix stream through this one) -- forward progress does not
+        // depend on the whole grid being resident.
+        s_role = atomicAdd(p.ticket + 2, 1u);
+        if (s_role != 0) {
             for (uint32_t e = 0; e <= (uint32_t) S; ++e)
                 draw(e, atomicAdd(scan_ticket, 1u));
             for (uint32_t e = 0; e < (uint32_t) S; ++e)
@@ -1077,12 +1083,12 @@ scan_ahead_kernel(const FastParams p) {
     }
     __syncthreads();
 
-    // ---- PREFIX stream (the last CTA of the grid, one warp): the running reduction over the tile aggregates, in
+    // ---- PREFIX stream (the first CTA to start, one warp): the running reduction over the tile aggregates, in
     // tile order, batches of 32 * PW descriptors with the next batch's loads in flight -- one sequential
     // stream instead of a look-back per tile (no tile ever walks over its predecessors; the front of known
     // prefixes moves 32 * PW tiles per L2 round trip and stays far in front of the scan stream).  It turns
     // every AGGREGATE entry into the PREFIX entry (inclusive) that the prefix warps of the other CTAs wait for.
-    if (blockIdx.x == gridDim.x - 1) {
+    if (s_role == 0) {
         if (warp != 0)
             return;
         constexpr int PW = 8;
@@ -1568,7 +1574,7 @@ template <typename T, int Op, typename G> static int launch_ahead(const ScanCall
         return fail(B200_ERR_CUDA, "jit_block_prefix_reduce(): out of memory");
     B200_CUDA_CHECK(cudaMemsetAsync(scratch, 0, desc_bytes + 16, c.stream));
     p.desc = (uint64_t *) scratch;
-    p.ticket = (uint32_t *) ((uint8_t *) scratch + desc_bytes); // scan tickets, reduce tickets
+    p.ticket = (uint32_t *) ((uint8_t *) scratch + desc_bytes); // scan tickets, reduce tickets, CTA roles
     kernel<<<grid, BLOCK, SMEM, c.stream>>>(p);
     temp_free(scratch, c.stream);
     B200_LAUNCH_CHECK();
