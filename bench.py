@@ -517,9 +517,12 @@ def measure_e2e(torch, dr, dist, world, dev, n, n_global, calls, call, out_elems
     h2d = 4 * n
     d2h = sum(4 * out_elems(kind, bs) for kind, bs in calls)
 
+    free = [None, None]  # result buffer b may be overwritten once its D2H copy has finished
+
     def step():
+        # (the H2D of this step's input is ordered behind the previous step's kernels by the main stream; it
+        # overlaps the tail of the previous step's D2H traffic -- the two directions of the link are independent)
         dr.jit_memcpy_async(CUDA, d_x, h_x, 4 * n, stream=main)
-        free = [None, None]
         for c, (kind, bs) in enumerate(calls):
             b = c & 1
             if free[b] is not None:
@@ -531,16 +534,17 @@ def measure_e2e(torch, dr, dist, world, dev, n, n_global, calls, call, out_elems
             dr.jit_memcpy_async(CUDA, h_out[b], d_out[b], 4 * out_elems(kind, bs), stream=copy)
             free[b] = torch.cuda.Event()
             free[b].record(copy)
-        main.wait_stream(copy)
 
     for _ in range(W):
         step()
+    main.wait_stream(copy)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
     t0.record()
     for _ in range(K):
         step()
+    main.wait_stream(copy)  # every result of the K steps has reached the host
     t1.record()
     torch.cuda.synchronize()
     barrier()
@@ -553,7 +557,7 @@ def measure_e2e(torch, dr, dist, world, dev, n, n_global, calls, call, out_elems
             "pcie_GBs": (h2d + d2h) / (ms_step * 1e-3) / 1e9,
             "host": host_topology(),
             "note": "pinned host input -> H2D -> 28 C-ABI calls -> D2H of every result "
-                    "(copy stream overlapped with the kernels); PCIe bound.  pcie_GBs is PER RANK; at N > 1 "
+                    "(copy stream overlapped with the kernels, the next step's H2D with the tail of the D2H traffic); PCIe bound.  pcie_GBs is PER RANK; at N > 1 "
                     "the ranks share the host's memory system (the 8-GPU boxes of this pool expose ONE NUMA "
                     "node with 32 cores to all GPUs -- profiles/r2_topo_n8.txt -- so there is nothing to bind "
                     "a rank to: the aggregate of ~96 GB/s is the host's limit)"}
