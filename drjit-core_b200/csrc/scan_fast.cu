@@ -1104,7 +1104,11 @@ scan_ahead_kernel(const FastParams p) {
                     s[w] = Desc<V>::observe(p.desc, idx, v[w]);
             }
         };
-        V carry = R::identity();
+        // float prefixes are carried in double: up to 2^19 tile aggregates are chained here, and a float chain
+        // would spend a good part of the 1e-5 the scan promises (as the block-cyclic offsets above)
+        using A = typename std::conditional<std::is_same<V, float>::value, double, V>::type;
+        using RA = Red<A, Op>;
+        A carry = RA::identity();
         fetch(0, val, st);
         for (uint32_t base = 0; base < p.ntiles; base += 32 * PW) {
             // all entries of the batch must be there (the reduce stream is usually far ahead)
@@ -1132,27 +1136,27 @@ scan_ahead_kernel(const FastParams p) {
                 const uint32_t idx = base + 32 * w + lane;
                 // block starts (and tile 0) hold their inclusive prefix already
                 const bool head = ((idx + p.tile_off) & p.seg_mask) == 0 || idx == 0;
-                V v = val[w];
+                A v = (A) val[w];
                 bool f = head;
                 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const V uv = shfl_up(v, d);
+                    const A uv = shfl_up(v, d);
                     const bool uf = __shfl_up_sync(FULL_MASK, (int) f, d) != 0;
                     if (lane >= (uint32_t) d) {
                         if (!f)
-                            v = R::apply(uv, v);
+                            v = RA::apply(uv, v);
                         f = f || uf;
                     }
                 }
                 if (!f)
-                    v = R::apply(carry, v);
+                    v = RA::apply(carry, v);
                 carry = shfl_idx(v, 31);
                 if (idx < p.ntiles) {
                     // (block starts were published as prefixes by the reduce stream)
                     if (((idx + p.tile_off) & p.seg_mask) != 0)
-                        Desc<V>::publish(p.desc, idx, DESC_PREFIX, v);
+                        Desc<V>::publish(p.desc, idx, DESC_PREFIX, (V) v);
                     if (p.carry_out && idx == p.ntiles - 1)
-                        *(V *) p.carry_out = v;
+                        *(V *) p.carry_out = (V) v;
                 }
             }
             #pragma unroll
