@@ -996,14 +996,19 @@ struct SpinGuard {
 // after the tile has landed (the tiles in front of it land at about the same time, have to be reduced and
 // published, and the prefix front hops over them one L2 round trip at a time), and the ring plus the
 // registers of a CTA cannot hold three more microseconds of the stream.  Here the reduction of a tile is
-// taken out of that chain: a REDUCE stream (one warp per CTA, its own ticket counter and a ring of
-// half-tile bulk copies) runs `lag` tiles (tens of MB) AHEAD of the SCAN stream, publishing tile aggregates;
-// the scan stream finds every aggregate it needs long published, its tiles still resident in the 126 MB L2
-// (they were read from HBM moments ago), and its look-back warp starts when a tile's ticket is DRAWN -- one
-// step before its load is requested, three before the compute warps reach it.  HBM traffic stays at 8 B per
-// element (read once by the reduce stream, written once); the second read is an L2 hit.  Correctness does
-// not depend on the lag (the look-back protocol waits for whatever is missing); the reduce stream throttles
-// itself so that its read-ahead stays inside L2.
+// taken out of that chain.  Three streams, all fed by tickets (tiles and roles go to CTAs in the order in
+// which they ask, so whatever a CTA waits for is owned by a CTA that is already running):
+//   REDUCE  one warp per CTA, its own ticket counter and a ring of half-tile bulk copies, runs `lag` tiles
+//           (tens of MB) AHEAD of the scan and publishes tile aggregates.  It throttles itself against the
+//           scan's ticket counter so that its read-ahead stays inside the 126 MB L2 -- without ever blocking.
+//   PREFIX  one warp of the first CTA to start: the running reduction over the aggregates, in tile order,
+//           256 descriptors per batch.  It turns every AGGREGATE descriptor into an (inclusive) PREFIX: no
+//           tile walks over its predecessors (the look-back of the kernel above), summation order is fixed.
+//   SCAN    the streaming kernel with a ring of two slots.  Its tiles were read from HBM moments ago (the second
+//           read is an L2 hit: HBM traffic stays at 8 B per element), and its prefix warp only waits for the
+//           descriptor in front of a tile to become a PREFIX -- from the moment the tile's ticket is DRAWN, one
+//           step before its load is requested, three before the compute warps reach it.
+// Correctness does not depend on the lag: every wait is on a descriptor that some running CTA will publish.
 template <typename T, int Op, int J, int S, int RS, int THREADS>
 __global__ void __launch_bounds__(THREADS + 64, 2)
 scan_ahead_kernel(const FastParams p) {
